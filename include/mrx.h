@@ -1,0 +1,145 @@
+/*
+ * mrx.h -- C ABI of the B200 (sm_100a) Mask R-CNN serving hot path.
+ *
+ * The reference (huyhoang17/matterport-maskrcnn-with-tensorflow-serving) has NO
+ * FFI / plugin interface: its boundary is three plain Python call sites in
+ * serve.py.  Each entry point below names the Python call it stands behind:
+ *
+ *   mrx_anchors            <- api_utils.get_anchors(image_shape)          serve.py:105
+ *   mrx_unmold_prologue    <- api_utils.unmold_detections(...) steps 1-6  serve.py:147-154
+ *   mrx_gather_tiles       <- mrcnn_mask[arange(N),:,:,class_ids]         (same call)
+ *   mrx_mask_expand        <- per-instance unmold_mask + np.stack(axis=-1)(same call)
+ *   mrx_cv2_resize_u8c3    <- cv2.resize(img, (S, S))                     serve.py:88-89
+ *   mrx_mold_image         <- resize_image + mold_image                   serve.py:91-98
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (the Python
+ *     side holds them as torch tensors and passes data_ptr()); nothing here
+ *     allocates, frees or synchronises -- all work is ordered on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - return value: MRX_OK (0) or a negative MRX_E_* code; mrx_last_error()
+ *     returns a thread-local description of the last failure.
+ *   - dtype codes: MRX_F32 = 0, MRX_F64 = 1.
+ *   - there is no CPU fallback behind any of these calls.
+ */
+#ifndef MRX_H_
+#define MRX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRX_ABI_VERSION 1
+
+#define MRX_OK              0
+#define MRX_E_INVALID      -1   /* bad argument (null pointer, size out of range) */
+#define MRX_E_UNSUPPORTED  -2   /* shape outside what the kernels are built for   */
+#define MRX_E_CUDA         -3   /* a CUDA runtime call failed                      */
+
+#define MRX_F32 0
+#define MRX_F64 1
+
+/* per-image status bits written by mrx_unmold_prologue into d_status[b] */
+#define MRX_ST_CLASS_RANGE  1   /* class id outside [-C, C): numpy would raise IndexError */
+#define MRX_ST_BOX_RANGE    2   /* kept box outside the canvas: numpy paste would raise   */
+
+/* limits (compile-time properties of the kernels) */
+#define MRX_MAX_LEVELS   8
+#define MRX_MAX_RATIOS   8
+#define MRX_MAX_BATCH    4096    /* images per mrx_mask_expand launch */
+#define MRX_MAX_MASK_DIM 64      /* mask tile side (28 upstream); width must be a multiple of 4 */
+
+int         mrx_abi_version(void);
+const char *mrx_last_error(void);
+
+/* Device properties the host-side planner needs (SM count, opt-in smem per block). */
+int mrx_device_props(int device, int *sm_count, int *cc_major, int *cc_minor,
+                     int *max_smem_optin);
+
+/* ---------------------------------------------------------------- anchors (a5) */
+/* Number of anchors for an image of img_h x img_w:  R * sum_l ceil(ceil(H/s_l)/as) * ceil(ceil(W/s_l)/as). */
+int mrx_anchor_count(int img_h, int img_w, const int *strides, int n_levels,
+                     int n_ratios, int anchor_stride, long long *count);
+
+/* d_out: [A,4] float32 (y1,x1,y2,x2) normalised by norm_boxes; level-major, then
+ * y, x, ratio innermost.  scales[n_levels], ratios[n_ratios] are HOST arrays.
+ * Arithmetic is fp64 with numpy's operation order, rounded once to fp32. */
+int mrx_anchors(float *d_out, int img_h, int img_w,
+                const double *scales, const double *ratios, const int *strides,
+                int n_levels, int n_ratios, int anchor_stride, void *stream);
+
+/* ---------------------------------------------------------------- unmold (a1-a4) */
+/* Geometry per image, 8 x int32:
+ *   [0] orig_h [1] orig_w   original image (canvas) size
+ *   [2] img_h  [3] img_w    molded image size
+ *   [4..7]  window y1,x1,y2,x2 in molded pixels                                  */
+#define MRX_GEOM_INTS 8
+
+/* Steps 1-6 of unmold_detections for a batch of B images, one CTA per image:
+ * trim at the first class_id==0 row, class ids, window normalisation (float32),
+ * box affine + denorm (float64, round-half-even), zero-area drop with
+ * order-preserving compaction.
+ *   d_detections [B,R,6] det_dtype      d_geom [B,8] int32
+ *   d_boxes [B,R,4] int32   d_class_ids [B,R] int32   d_scores [B,R] det_dtype
+ *   d_src_index [B,R] int32 (kept row -> original row)
+ *   d_counts [B] int32 (N per image)    d_status [B] int32 (MRX_ST_* bits)
+ * C = number of classes in mrcnn_mask's last axis (for the class-range check).
+ * Also resets *d_job_counter (uint32) used by mrx_mask_expand's scheduler. */
+int mrx_unmold_prologue(const void *d_detections, int det_dtype, int B, int R, int C,
+                        const int *d_geom,
+                        int *d_boxes, int *d_class_ids, void *d_scores,
+                        int *d_src_index, int *d_counts, int *d_status,
+                        unsigned int *d_job_counter, void *stream);
+
+/* masks = mrcnn_mask[src_index, :, :, class_id] packed to float32 tiles.
+ *   d_mrcnn_mask [B,R,mh,mw,C] mask_dtype  ->  d_tiles [B,R,mh,mw] float32      */
+int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype,
+                     int B, int R, int mh, int mw, int C,
+                     const int *d_class_ids, const int *d_src_index,
+                     const int *d_counts, float *d_tiles, void *stream);
+
+/* The hot kernel.  For every image b writes the bool canvas [H_b, W_b, N_b]
+ * (N innermost, 1 byte per element, values 0/1) at d_canvas + d_canvas_off[b]:
+ * zero fill, zero-border half-pixel bilinear resize of each tile to its box,
+ * >= 0.5 threshold and paste, fused so each output byte is written once.
+ *   d_canvas_off [B] int64, each a multiple of 16; slot b must hold at least
+ *   round_up(H_b*W_b*N_b, 16) bytes (the pad bytes are written as 0).
+ *   chunk_bytes: bytes of canvas one CTA builds in shared memory and stores
+ *   with one bulk copy; multiple of 16; 0 = library default.
+ *   ctas_per_sm: 0 = as many as fit.                                              */
+int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_counts,
+                    const int *d_geom, const long long *d_canvas_off,
+                    unsigned char *d_canvas, int B, int R, int mh, int mw,
+                    int chunk_bytes, int ctas_per_sm,
+                    unsigned int *d_job_counter, void *stream);
+
+/* Pre-threshold resized values of one instance (test hook for the stated fp32
+ * tolerance): d_out [bh, bw] float32 for box (y1,x1,y2,x2); uses the same device
+ * sampling routine as mrx_mask_expand. */
+int mrx_resize_tile_f32(const float *d_tile, int mh, int mw, int bh, int bw,
+                        float *d_out, void *stream);
+
+/* ---------------------------------------------------------------- mold (a6) */
+/* cv2.resize(src, (dst_w, dst_h)) for uint8 HxWx3, default INTER_LINEAR
+ * (OpenCV's 11-bit fixed-point path, incl. its exact-2x INTER_AREA shortcut). */
+int mrx_cv2_resize_u8c3(const unsigned char *d_src, int src_h, int src_w,
+                        unsigned char *d_dst, int dst_h, int dst_w, void *stream);
+
+/* resize_image(mode square/pad64/none geometry precomputed by the host) fused
+ * with mold_image: scale src (uint8 HxWx3) to new_h x new_w with the zero-border
+ * bilinear of a4 in fp64, truncate to uint8, place at (top,left) in an
+ * out_h x out_w canvas of zeros, subtract mean_pixel.
+ *   out_dtype MRX_F32: float32( float64(u8) - mean )   (what serve.py:117 sends)
+ *   out_dtype MRX_F64: float64(u8) - mean              (what preprocess_input returns)
+ *   d_molded_u8 (optional, may be NULL): the uint8 image before mean subtraction. */
+int mrx_mold_image(const unsigned char *d_src, int src_h, int src_w,
+                   int new_h, int new_w, int top, int left, int out_h, int out_w,
+                   const double *mean_pixel /* host, 3 */, int out_dtype,
+                   void *d_out, unsigned char *d_molded_u8, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRX_H_ */

@@ -1,0 +1,591 @@
+// unmold.cu -- the serving post-processing path of the reference,
+// api_utils.unmold_detections (/root/reference/serve.py:147-154), as sm_100a kernels.
+//
+//   unmold_prologue_kernel   steps 1-6 of the upstream body (trim, class ids, window
+//                            normalisation, box affine + denorm, zero-area compaction)
+//   gather_tiles_kernel      masks = mrcnn_mask[arange(N), :, :, class_ids]  -> packed fp32
+//   mask_expand_kernel       per-instance resize + threshold + paste + np.stack(axis=-1),
+//                            fused: one bulk (TMA) store per chunk of the [H,W,N] canvas
+//
+// Data layout in HBM (all row-major, caller-owned):
+//   detections [B,R,6] f32|f64        mrcnn_mask [B,R,mh,mw,C] f32|f64
+//   boxes [B,R,4] i32   class_ids/src_index [B,R] i32   scores [B,R]   counts/status [B]
+//   tiles [B,R,mh,mw] f32 (selected class only, 3136 B per instance at 28x28)
+//   canvas: image b at canvas + canvas_off[b], bytes [H_b, W_b, N_b] (N innermost)
+#include "common.cuh"
+
+namespace mrx {
+
+// =====================================================================================
+// prologue: one CTA per image
+// =====================================================================================
+constexpr int kPrologueThreads = 128;
+
+template <typename T>
+struct BoxAffine;
+
+// detections arrive as float64 (serve.py:131-136 builds them from Python floats):
+//   boxes(float64) - shift(float32 array) -> float64 ; / scale(float32 array) -> float64
+template <>
+struct BoxAffine<double> {
+  __device__ static double apply(double v, float shift, float scale) {
+    return __ddiv_rn(__dsub_rn(v, static_cast<double>(shift)), static_cast<double>(scale));
+  }
+};
+// float32 detections: numpy keeps the affine in float32, widening only in denorm_boxes
+template <>
+struct BoxAffine<float> {
+  __device__ static double apply(float v, float shift, float scale) {
+    return static_cast<double>(__fdiv_rn(__fsub_rn(v, shift), scale));
+  }
+};
+
+__device__ __forceinline__ float norm_coord_f32(int v, int shift, int extent_minus_1) {
+  // utils.norm_boxes: (int - int) / int in float64, then astype(float32)
+  return __double2float_rn(
+      __ddiv_rn(static_cast<double>(v - shift), static_cast<double>(extent_minus_1)));
+}
+
+__device__ __forceinline__ int denorm_coord(double v, int extent_minus_1, int shift) {
+  // utils.denorm_boxes: around(v * (extent-1) + shift).astype(int32); around = half-to-even
+  const double t = __dadd_rn(__dmul_rn(v, static_cast<double>(extent_minus_1)),
+                             static_cast<double>(shift));
+  return __double2int_rn(t);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPrologueThreads)
+unmold_prologue_kernel(const T *__restrict__ det, int R, int C,
+                       const int *__restrict__ geom, int *__restrict__ boxes,
+                       int *__restrict__ class_ids, T *__restrict__ scores,
+                       int *__restrict__ src_index, int *__restrict__ counts,
+                       int *__restrict__ status, unsigned int *__restrict__ job_counter) {
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  constexpr int kWarps = kPrologueThreads / 32;
+
+  __shared__ int s_first_zero;
+  __shared__ int s_status;
+  __shared__ int s_wcnt[kWarps];
+
+  if (tid == 0) {
+    s_first_zero = R;
+    s_status = 0;
+    if (b == 0 && job_counter != nullptr) *job_counter = 0u;
+  }
+  __syncthreads();
+
+  const T *d = det + static_cast<size_t>(b) * R * 6;
+  // step 1: N = index of the first row whose class_id == 0 (zero padding), else R
+  for (int t = tid; t < R; t += kPrologueThreads) {
+    if (d[t * 6 + 4] == T(0)) atomicMin(&s_first_zero, t);
+  }
+  __syncthreads();
+  const int n_trim = s_first_zero;
+
+  // step 3: window = norm_boxes(window, image_shape[:2]) -> float32
+  const int *g = geom + b * MRX_GEOM_INTS;
+  const int orig_h = g[0], orig_w = g[1], img_h = g[2], img_w = g[3];
+  const float wy1 = norm_coord_f32(g[4], 0, img_h - 1);
+  const float wx1 = norm_coord_f32(g[5], 0, img_w - 1);
+  const float wy2 = norm_coord_f32(g[6], 1, img_h - 1);
+  const float wx2 = norm_coord_f32(g[7], 1, img_w - 1);
+  const float wh = __fsub_rn(wy2, wy1);  // np.float32 scalar arithmetic
+  const float ww = __fsub_rn(wx2, wx1);
+
+  int running = 0;
+  int my_status = 0;
+  for (int base = 0; base < n_trim; base += kPrologueThreads) {
+    const int t = base + tid;
+    bool keep = false;
+    int y1 = 0, x1 = 0, y2 = 0, x2 = 0, cls = 0;
+    T score = T(0);
+    if (t < n_trim) {
+      const T *row = d + t * 6;
+      // steps 4-5: affine into the window, then pixels of the original image
+      y1 = denorm_coord(BoxAffine<T>::apply(row[0], wy1, wh), orig_h - 1, 0);
+      x1 = denorm_coord(BoxAffine<T>::apply(row[1], wx1, ww), orig_w - 1, 0);
+      y2 = denorm_coord(BoxAffine<T>::apply(row[2], wy1, wh), orig_h - 1, 1);
+      x2 = denorm_coord(BoxAffine<T>::apply(row[3], wx1, ww), orig_w - 1, 1);
+      cls = static_cast<int>(row[4]);  // astype(int32): truncation
+      score = row[5];
+      // step 6: drop rows with (y2 - y1) * (x2 - x1) <= 0   (int32 arithmetic)
+      keep = ((y2 - y1) * (x2 - x1)) > 0;
+      // numpy fancy indexing accepts class ids in [-C, C)
+      if (cls < -C || cls >= C) my_status |= MRX_ST_CLASS_RANGE;
+      if (keep && (y1 < 0 || x1 < 0 || y2 > orig_h || x2 > orig_w || y2 <= y1 || x2 <= x1))
+        my_status |= MRX_ST_BOX_RANGE;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = running, total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const int c = s_wcnt[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    if (keep) {
+      const int pos = before + __popc(bal & ((1u << lane) - 1u));
+      const size_t o = static_cast<size_t>(b) * R + pos;
+      reinterpret_cast<int4 *>(boxes)[o] = make_int4(y1, x1, y2, x2);
+      class_ids[o] = cls;
+      scores[o] = score;
+      src_index[o] = t;
+    }
+    running += total;
+    __syncthreads();
+  }
+  if (my_status) atomicOr(&s_status, my_status);
+  __syncthreads();
+  if (tid == 0) {
+    counts[b] = running;
+    status[b] = s_status;
+  }
+}
+
+// =====================================================================================
+// class-tile gather: grid (R, B), one CTA per (image, kept instance)
+// =====================================================================================
+constexpr int kGatherThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_tiles_kernel(const T *__restrict__ mask, int R, int tile_elems, int C,
+                    const int *__restrict__ class_ids, const int *__restrict__ src_index,
+                    const int *__restrict__ counts, float *__restrict__ tiles) {
+  const int k = blockIdx.x;
+  const int b = blockIdx.y;
+  if (k >= counts[b]) return;
+  const size_t o = static_cast<size_t>(b) * R + k;
+  int cls = class_ids[o];
+  if (cls < 0) cls += C;               // numpy negative index wrap
+  if (cls < 0 || cls >= C) cls = 0;    // flagged by the prologue; stay in bounds
+  const int src = src_index[o];
+  const T *in = mask + (static_cast<size_t>(b) * R + src) * tile_elems * C + cls;
+  float *out = tiles + o * tile_elems;
+  for (int p = threadIdx.x; p < tile_elems; p += kGatherThreads)
+    out[p] = static_cast<float>(in[static_cast<size_t>(p) * C]);
+}
+
+// =====================================================================================
+// mask expand: persistent CTAs, each builds one chunk of a canvas in shared memory
+// =====================================================================================
+//
+// A job is `chunk_bytes` consecutive bytes of one image's [H,W,N] canvas (flat byte
+// stream; N innermost so a pixel is N consecutive bytes).  Per job the CTA
+//   1. lists the (box, row) pairs that intersect the chunk            -> entries
+//   2. stages the two tile rows each entry interpolates between with a 1-D TMA bulk
+//      copy (224 B at mw = 28) and blends them vertically in place
+//   3. walks each entry's x-span: exact integer source coordinate, fp32 lerp of the
+//      blended row, >= 0.5, byte store into the shared-memory chunk
+//   4. hands the chunk to the TMA with one bulk store (HBM sees one write per byte)
+// Zero fill is the memset of the shared chunk, skipped when the previous job left it
+// all-zero.
+constexpr int kExpandThreads = 256;
+constexpr int kExpandWarps = kExpandThreads / 32;
+constexpr int kEMax = 128;  // entries per pass == pairs tested per pass
+
+struct __align__(16) Entry {
+  int n;       // instance index (position along the innermost canvas axis)
+  int row;     // canvas row
+  int xa, xb;  // span [xa, xb) of canvas columns inside the chunk and the box
+  int x1;      // box left
+  int bw;      // box width
+  int j0;      // floor of the source row coordinate, in [-1, mh-1]
+  float wy;    // its fractional part
+};
+
+struct ExpandParams {
+  const float *tiles;
+  const int4 *boxes;
+  const int *counts;
+  const int *geom;
+  const long long *canvas_off;
+  unsigned char *canvas;
+  unsigned int *job_counter;
+  int B, R, mh, mw, chunk_bytes;
+};
+
+__global__ void __launch_bounds__(kExpandThreads)
+mask_expand_kernel(const ExpandParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int mh = p.mh, mw = p.mw;
+  const int slot_floats = 2 * mw;             // two tile rows; reused for the blended row
+  const uint32_t slot_bytes = slot_floats * 4;
+
+  // ---- carve shared memory
+  unsigned char *s_out = smem;                                        // chunk_bytes
+  float *s_stage = reinterpret_cast<float *>(smem + p.chunk_bytes);   // kEMax slots
+  Entry *s_entry = reinterpret_cast<Entry *>(s_stage + kEMax * slot_floats);
+  int *s_jobs = reinterpret_cast<int *>(s_entry + kEMax);             // B + 1 prefix
+  __shared__ uint64_t s_bar;
+  __shared__ int s_count[2];
+  __shared__ int s_jobid;
+  __shared__ int s_carry;
+
+  // ---- job table: jobs_b = ceil(H*W*N_b / chunk); exclusive prefix in s_jobs
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base < p.B; base += 32) {
+      const int b = base + lane;
+      int v = 0;
+      if (b < p.B) {
+        const long long bytes = static_cast<long long>(p.geom[b * MRX_GEOM_INTS + 0]) *
+                                p.geom[b * MRX_GEOM_INTS + 1] * p.counts[b];
+        v = static_cast<int>((bytes + p.chunk_bytes - 1) / p.chunk_bytes);
+      }
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (b < p.B) s_jobs[b + 1] = carry + incl;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      s_jobs[0] = 0;
+      s_carry = carry;
+    }
+  }
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+    s_count[0] = 0;
+    s_count[1] = 0;
+  }
+  __syncthreads();
+  const int total_jobs = s_carry;
+
+  uint32_t bar_parity = 0;
+  int pass_parity = 0;
+  int cur_b = 0;
+  bool dirty = true;          // shared chunk not known to be all-zero yet
+  int next_job = 0;
+  if (tid == 0) next_job = static_cast<int>(atomicAdd(p.job_counter, 1u));
+
+  while (true) {
+    if (tid == 0) {
+      s_jobid = next_job;
+      bulk_wait_read<0>();    // the previous chunk has left shared memory
+    }
+    __syncthreads();          // (S1) job id visible, s_out reusable, staging reusable
+    const int job = s_jobid;
+    if (job >= total_jobs) break;
+    if (tid == 0) next_job = static_cast<int>(atomicAdd(p.job_counter, 1u));
+
+    while (job >= s_jobs[cur_b + 1]) ++cur_b;
+    const int b = cur_b;
+    const int H = p.geom[b * MRX_GEOM_INTS + 0];
+    const int W = p.geom[b * MRX_GEOM_INTS + 1];
+    const int N = p.counts[b];
+    const long long L = static_cast<long long>(H) * W * N;
+    const long long c0 = static_cast<long long>(job - s_jobs[b]) * p.chunk_bytes;
+    const int len = static_cast<int>(min(static_cast<long long>(p.chunk_bytes), L - c0));
+    const int len16 = (len + 15) & ~15;
+    const int g0 = static_cast<int>(c0 / N);                 // first pixel touched
+    const int g1 = static_cast<int>((c0 + len - 1) / N);     // last pixel touched
+    const int r0 = g0 / W;
+    const int r1 = g1 / W;
+    const int n_pairs = (r1 - r0 + 1) * N;
+    const int sub = static_cast<int>(c0 - static_cast<long long>(g0) * N);  // bytes of pixel g0 before c0
+    const float *tiles_b = p.tiles + static_cast<size_t>(b) * p.R * mh * mw;
+    const int4 *boxes_b = p.boxes + static_cast<size_t>(b) * p.R;
+
+    // ---- zero fill (memset of the shared chunk)
+    if (dirty) {
+      uint4 *o4 = reinterpret_cast<uint4 *>(s_out);
+      const int n16 = len16 >> 4;
+      for (int i = tid; i < n16; i += kExpandThreads) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    bool wrote = false;
+
+    for (int p0 = 0; p0 < n_pairs; p0 += kEMax) {
+      if (p0 > 0) {
+        fence_proxy_async_smem();   // generic accesses to staging before the next TMA fill
+        __syncthreads();
+      }
+      // ---- 1. entries: thread t tests pair p0 + t
+      if (tid < kEMax) {
+        const int pr = p0 + tid;
+        bool valid = false;
+        Entry e;
+        if (pr < n_pairs) {
+          const int dr = pr / N;
+          const int n = pr - dr * N;
+          const int row = r0 + dr;
+          const int4 bx = __ldg(boxes_b + n);   // (y1, x1, y2, x2)
+          const int xlo = max(0, g0 - row * W);
+          const int xhi = min(W, g1 + 1 - row * W);
+          const int xa = max(xlo, bx.y);
+          const int xb = min(xhi, bx.w);
+          const bool sane = bx.x >= 0 && bx.y >= 0 && bx.z <= H && bx.w <= W;
+          valid = sane && row >= bx.x && row < bx.z && xa < xb;
+          if (valid) {
+            const int bh = bx.z - bx.x;
+            const int Dy = 2 * bh;
+            const int Ay = mh * (2 * (row - bx.x) + 1) - bh;
+            const int j0 = floor_div(Ay, Dy);
+            e.n = n;
+            e.row = row;
+            e.xa = xa;
+            e.xb = xb;
+            e.x1 = bx.y;
+            e.bw = bx.w - bx.y;
+            e.j0 = j0;
+            e.wy = __fdiv_rn(static_cast<float>(Ay - j0 * Dy), static_cast<float>(Dy));
+          }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&s_count[pass_parity], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (valid) {
+          const int slot = base + __popc(bal & ((1u << lane) - 1u));
+          s_entry[slot] = e;
+          // ---- 2a. stage rows jc, jc+1 of the tile (jc clamps j0 into [0, mh-2])
+          const int jc = min(max(e.j0, 0), mh - 2);
+          bulk_g2s(s_stage + slot * slot_floats,
+                   tiles_b + (static_cast<size_t>(e.n) * mh + jc) * mw, slot_bytes, &s_bar);
+        }
+      }
+      __syncthreads();   // (S2) entries + count visible; zero fill complete
+      const int E = s_count[pass_parity];
+      if (tid == 0) {
+        s_count[pass_parity ^ 1] = 0;
+        if (E > 0) mbar_arrive_expect_tx(&s_bar, E * slot_bytes);
+      }
+      pass_parity ^= 1;
+      if (E == 0) continue;
+      wrote = true;
+      mbar_wait(&s_bar, bar_parity);
+      bar_parity ^= 1;
+
+      // ---- 2b + 3. one warp per entry: vertical blend in place, then the x-span
+      for (int ei = warp; ei < E; ei += kExpandWarps) {
+        const Entry e = s_entry[ei];
+        float *slot = s_stage + ei * slot_floats;
+        {
+          const int jc = min(max(e.j0, 0), mh - 2);
+          // slot rows: a = tile row jc, bq = tile row jc+1
+          float v0 = 0.f, v1 = 0.f;   // lane handles columns lane and lane + 32
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;
+            if (i < mw) {
+              const float a = slot[i];
+              const float bq = slot[mw + i];
+              const float top = (e.j0 < 0) ? 0.f : ((e.j0 == jc) ? a : bq);
+              const float bot = (e.j0 + 1 > mh - 1) ? 0.f : ((e.j0 + 1 == jc) ? a : bq);
+              const float v = fmaf(e.wy, bot - top, top);
+              if (h == 0) v0 = v; else v1 = v;
+            }
+          }
+          __syncwarp();
+          // blended row with a zero on each side: slot[0] = 0, slot[1+i] = v_i, slot[mw+1] = 0
+          if (lane < mw) slot[1 + lane] = v0;
+          if (lane + 32 < mw) slot[1 + lane + 32] = v1;
+          if (lane == 0) {
+            slot[0] = 0.f;
+            slot[mw + 1] = 0.f;
+          }
+          __syncwarp();
+        }
+        const float inv_2bw = __fdiv_rn(1.0f, static_cast<float>(2 * e.bw));
+        // byte offset of (row, x, n) inside the chunk = obase + x * N
+        const int obase = (e.row * W - g0) * N + e.n - sub;
+        for (int x = e.xa + lane; x < e.xb; x += 32) {
+          const SrcCoord sc = src_coord(x - e.x1, mw, e.bw, inv_2bw);
+          const float a = slot[sc.i0 + 1];
+          const float bq = slot[sc.i0 + 2];
+          const float v = fmaf(sc.w, bq - a, a);
+          const int off = obase + x * N;
+          if (v >= 0.5f && static_cast<unsigned>(off) < static_cast<unsigned>(len))
+            s_out[off] = 1;
+        }
+      }
+    }
+
+    // ---- 4. hand the chunk to the TMA
+    fence_proxy_async_smem();
+    __syncthreads();   // (S3)
+    if (tid == 0) {
+      bulk_s2g(p.canvas + p.canvas_off[b] + c0, s_out, static_cast<uint32_t>(len16));
+      bulk_commit();
+    }
+    dirty = wrote;
+  }
+  if (tid == 0) bulk_wait_all<0>();
+}
+
+// =====================================================================================
+// test hook: pre-threshold values of one resized tile, same sampling code
+// =====================================================================================
+__global__ void resize_tile_kernel(const float *__restrict__ tile, int mh, int mw, int bh,
+                                   int bw, float *__restrict__ out) {
+  const int y = blockIdx.x;
+  const int Dy = 2 * bh;
+  const int Ay = mh * (2 * y + 1) - bh;
+  const int j0 = floor_div(Ay, Dy);
+  const float wy = __fdiv_rn(static_cast<float>(Ay - j0 * Dy), static_cast<float>(Dy));
+  extern __shared__ float s_row[];   // mw + 2
+  for (int i = threadIdx.x; i < mw + 2; i += blockDim.x) {
+    float v = 0.f;
+    if (i >= 1 && i <= mw) {
+      const float top = (j0 < 0) ? 0.f : tile[j0 * mw + (i - 1)];
+      const float bot = (j0 + 1 > mh - 1) ? 0.f : tile[(j0 + 1) * mw + (i - 1)];
+      v = fmaf(wy, bot - top, top);
+    }
+    s_row[i] = v;
+  }
+  __syncthreads();
+  const float inv_2bw = __fdiv_rn(1.0f, static_cast<float>(2 * bw));
+  for (int x = threadIdx.x; x < bw; x += blockDim.x) {
+    const SrcCoord sc = src_coord(x, mw, bw, inv_2bw);
+    const float a = s_row[sc.i0 + 1];
+    const float bq = s_row[sc.i0 + 2];
+    out[static_cast<size_t>(y) * bw + x] = fmaf(sc.w, bq - a, a);
+  }
+}
+
+}  // namespace mrx
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+using namespace mrx;
+
+static int check_mask_dims(int mh, int mw) {
+  MRX_CHECK_SUPPORTED(mh >= 2 && mh <= MRX_MAX_MASK_DIM && mw >= 4 && mw <= MRX_MAX_MASK_DIM &&
+                          (mw % 4) == 0,
+                      "mask tile %dx%d unsupported (need 2<=mh<=%d, 4<=mw<=%d, mw%%4==0)", mh,
+                      mw, MRX_MAX_MASK_DIM, MRX_MAX_MASK_DIM);
+  return MRX_OK;
+}
+
+extern "C" int mrx_unmold_prologue(const void *d_detections, int det_dtype, int B, int R, int C,
+                                   const int *d_geom, int *d_boxes, int *d_class_ids,
+                                   void *d_scores, int *d_src_index, int *d_counts,
+                                   int *d_status, unsigned int *d_job_counter, void *stream) {
+  MRX_CHECK_ARG(d_detections && d_geom && d_boxes && d_class_ids && d_scores && d_src_index &&
+                    d_counts && d_status,
+                "mrx_unmold_prologue: null pointer");
+  MRX_CHECK_ARG(B >= 0 && R >= 1 && C >= 1, "mrx_unmold_prologue: bad sizes B=%d R=%d C=%d", B,
+                R, C);
+  MRX_CHECK_ARG(det_dtype == MRX_F32 || det_dtype == MRX_F64,
+                "mrx_unmold_prologue: det_dtype %d", det_dtype);
+  if (B == 0) return MRX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (det_dtype == MRX_F64) {
+    unmold_prologue_kernel<double><<<B, kPrologueThreads, 0, st>>>(
+        static_cast<const double *>(d_detections), R, C, d_geom, d_boxes, d_class_ids,
+        static_cast<double *>(d_scores), d_src_index, d_counts, d_status, d_job_counter);
+  } else {
+    unmold_prologue_kernel<float><<<B, kPrologueThreads, 0, st>>>(
+        static_cast<const float *>(d_detections), R, C, d_geom, d_boxes, d_class_ids,
+        static_cast<float *>(d_scores), d_src_index, d_counts, d_status, d_job_counter);
+  }
+  MRX_LAUNCH_CHECK("unmold_prologue_kernel");
+  return MRX_OK;
+}
+
+extern "C" int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype, int B, int R, int mh,
+                                int mw, int C, const int *d_class_ids, const int *d_src_index,
+                                const int *d_counts, float *d_tiles, void *stream) {
+  MRX_CHECK_ARG(d_mrcnn_mask && d_class_ids && d_src_index && d_counts && d_tiles,
+                "mrx_gather_tiles: null pointer");
+  MRX_CHECK_ARG(B >= 0 && R >= 1 && R <= 65535 && C >= 1 && mh >= 1 && mw >= 1,
+                "mrx_gather_tiles: bad sizes");
+  MRX_CHECK_ARG(B <= 65535, "mrx_gather_tiles: B=%d > 65535", B);
+  MRX_CHECK_ARG(mask_dtype == MRX_F32 || mask_dtype == MRX_F64, "mrx_gather_tiles: mask_dtype %d",
+                mask_dtype);
+  if (B == 0) return MRX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(R, B);
+  if (mask_dtype == MRX_F64) {
+    gather_tiles_kernel<double><<<grid, kGatherThreads, 0, st>>>(
+        static_cast<const double *>(d_mrcnn_mask), R, mh * mw, C, d_class_ids, d_src_index,
+        d_counts, d_tiles);
+  } else {
+    gather_tiles_kernel<float><<<grid, kGatherThreads, 0, st>>>(
+        static_cast<const float *>(d_mrcnn_mask), R, mh * mw, C, d_class_ids, d_src_index,
+        d_counts, d_tiles);
+  }
+  MRX_LAUNCH_CHECK("gather_tiles_kernel");
+  return MRX_OK;
+}
+
+extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_counts,
+                               const int *d_geom, const long long *d_canvas_off,
+                               unsigned char *d_canvas, int B, int R, int mh, int mw,
+                               int chunk_bytes, int ctas_per_sm, unsigned int *d_job_counter,
+                               void *stream) {
+  MRX_CHECK_ARG(d_tiles && d_boxes && d_counts && d_geom && d_canvas_off && d_canvas &&
+                    d_job_counter,
+                "mrx_mask_expand: null pointer");
+  MRX_CHECK_ARG(B >= 0 && B <= MRX_MAX_BATCH && R >= 1, "mrx_mask_expand: bad sizes B=%d R=%d",
+                B, R);
+  if (int rc = check_mask_dims(mh, mw)) return rc;
+  if (chunk_bytes == 0) chunk_bytes = 51200;
+  MRX_CHECK_ARG(chunk_bytes >= 1024 && (chunk_bytes % 16) == 0,
+                "mrx_mask_expand: chunk_bytes %d must be a multiple of 16, >= 1024", chunk_bytes);
+  if (B == 0) return MRX_OK;
+
+  int dev = 0;
+  MRX_CUDA(cudaGetDevice(&dev));
+  int sms = 0, max_optin = 0;
+  MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  MRX_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+
+  const size_t smem = static_cast<size_t>(chunk_bytes) +
+                      static_cast<size_t>(kEMax) * 2 * mw * sizeof(float) +
+                      static_cast<size_t>(kEMax) * sizeof(Entry) +
+                      static_cast<size_t>(B + 1) * sizeof(int);
+  MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(max_optin),
+                      "mrx_mask_expand: %zu B shared memory > device limit %d (chunk_bytes too "
+                      "large)",
+                      smem, max_optin);
+  MRX_CUDA(cudaFuncSetAttribute(mask_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  int occ = 0;
+  MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mask_expand_kernel,
+                                                         kExpandThreads, smem));
+  MRX_CHECK_SUPPORTED(occ >= 1, "mrx_mask_expand: kernel does not fit on an SM");
+  if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
+
+  ExpandParams prm;
+  prm.tiles = d_tiles;
+  prm.boxes = reinterpret_cast<const int4 *>(d_boxes);
+  prm.counts = d_counts;
+  prm.geom = d_geom;
+  prm.canvas_off = d_canvas_off;
+  prm.canvas = d_canvas;
+  prm.job_counter = d_job_counter;
+  prm.B = B;
+  prm.R = R;
+  prm.mh = mh;
+  prm.mw = mw;
+  prm.chunk_bytes = chunk_bytes;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  mask_expand_kernel<<<sms * occ, kExpandThreads, smem, st>>>(prm);
+  MRX_LAUNCH_CHECK("mask_expand_kernel");
+  return MRX_OK;
+}
+
+extern "C" int mrx_resize_tile_f32(const float *d_tile, int mh, int mw, int bh, int bw,
+                                   float *d_out, void *stream) {
+  MRX_CHECK_ARG(d_tile && d_out, "mrx_resize_tile_f32: null pointer");
+  MRX_CHECK_ARG(bh >= 1 && bw >= 1 && bh <= 65535, "mrx_resize_tile_f32: bad box %dx%d", bh, bw);
+  if (int rc = check_mask_dims(mh, mw)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  resize_tile_kernel<<<bh, 128, (mw + 2) * sizeof(float), st>>>(d_tile, mh, mw, bh, bw, d_out);
+  MRX_LAUNCH_CHECK("resize_tile_kernel");
+  return MRX_OK;
+}

@@ -1,0 +1,331 @@
+"""Device-resident engines over the C ABI (include/mrx.h).
+
+PyTorch tensors are used only as owners of device / pinned-host memory and for streams;
+every computation on the path is a libmrx kernel launched through ctypes.
+
+  UnmoldEngine     batched `unmold_detections` (serve.py:147-154): prologue -> class-tile
+                   gather -> fused mask expand, all stream-ordered, no host sync
+  AnchorGenerator  `get_anchors` (serve.py:105)
+  Molder           the body of `preprocess_input` (serve.py:83-107): cv2.resize + resize_image
+                   + mold_image
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _native as N
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dtype_code(np_dtype):
+    dt = np.dtype(np_dtype)
+    if dt == np.float32:
+        return N.MRX_F32
+    if dt == np.float64:
+        return N.MRX_F64
+    raise TypeError(f"unsupported floating dtype {dt}; use float32 or float64")
+
+
+def _torch_dtype(np_dtype):
+    torch = _torch()
+    return {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[
+        np.dtype(np_dtype)]
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def make_geom(original_image_shape, image_shape, window):
+    """Pack one image's geometry the way mrx_unmold_prologue expects (8 x int32)."""
+    oh, ow = int(original_image_shape[0]), int(original_image_shape[1])
+    ih, iw = int(image_shape[0]), int(image_shape[1])
+    wy1, wx1, wy2, wx2 = [int(v) for v in window]
+    return [oh, ow, ih, iw, wy1, wx1, wy2, wx2]
+
+
+class UnmoldEngine:
+    """Batched, device-resident `unmold_detections`.
+
+    Work buffers for up to `max_batch` images of up to `max_instances` detection rows are
+    allocated once; the canvas (bool [H,W,N] per image, N innermost) lives in one device
+    buffer with a fixed-capacity slot per image (capacity H*W*R rounded up to 256 B) so
+    that nothing on the path depends on a host read of the kept counts.
+    """
+
+    def __init__(self, max_batch, max_instances=100, mask_hw=(28, 28), num_classes=81,
+                 det_dtype=np.float32, mask_dtype=np.float32, device=None,
+                 chunk_bytes=0, ctas_per_sm=0):
+        N.require_cuda()
+        torch = _torch()
+        self.lib = N.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.B = int(max_batch)
+        self.R = int(max_instances)
+        self.mh, self.mw = int(mask_hw[0]), int(mask_hw[1])
+        self.C = int(num_classes)
+        self.det_dtype = np.dtype(det_dtype)
+        self.mask_dtype = np.dtype(mask_dtype)
+        self.chunk_bytes = int(chunk_bytes)
+        self.ctas_per_sm = int(ctas_per_sm)
+        if self.B < 1 or self.B > N.MRX_MAX_BATCH:
+            raise ValueError(f"max_batch must be in [1, {N.MRX_MAX_BATCH}]")
+        dev, i32 = self.device, torch.int32
+        B, R = self.B, self.R
+        self.d_boxes = torch.empty((B, R, 4), dtype=i32, device=dev)
+        self.d_class_ids = torch.empty((B, R), dtype=i32, device=dev)
+        self.d_scores = torch.empty((B, R), dtype=_torch_dtype(self.det_dtype), device=dev)
+        self.d_src_index = torch.empty((B, R), dtype=i32, device=dev)
+        self.d_counts = torch.zeros((B,), dtype=i32, device=dev)
+        self.d_status = torch.zeros((B,), dtype=i32, device=dev)
+        self.d_tiles = torch.empty((B, R, self.mh, self.mw), dtype=torch.float32, device=dev)
+        self.d_geom = torch.zeros((B, N.MRX_GEOM_INTS), dtype=i32, device=dev)
+        self.d_canvas_off = torch.zeros((B,), dtype=torch.int64, device=dev)
+        self.d_job_counter = torch.zeros((1,), dtype=i32, device=dev)
+        self.d_canvas = None
+        self._geom_host = None
+        self._offsets = None
+        self._n_images = 0
+
+    # ------------------------------------------------------------------ planning
+    def plan(self, geoms):
+        """Set the per-image geometry ([n,8] ints, see make_geom) and size the canvas."""
+        torch = _torch()
+        g = np.ascontiguousarray(np.asarray(geoms, dtype=np.int32).reshape(-1, N.MRX_GEOM_INTS))
+        n = g.shape[0]
+        if n < 1 or n > self.B:
+            raise ValueError(f"batch of {n} images does not fit max_batch={self.B}")
+        if self._geom_host is not None and self._geom_host.shape == g.shape and \
+                np.array_equal(self._geom_host, g):
+            return
+        if (g[:, :4] < 2).any():
+            raise ValueError("image sides must be >= 2")
+        if (g[:, 0].astype(np.int64) * g[:, 1] > (1 << 30)).any():
+            raise ValueError("canvas larger than 2^30 pixels is not supported")
+        cap = (g[:, 0].astype(np.int64) * g[:, 1].astype(np.int64) * self.R + 255) // 256 * 256
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(cap, out=off[1:])
+        total = int(off[-1])
+        if self.d_canvas is None or self.d_canvas.numel() < total:
+            self.d_canvas = None
+            self.d_canvas = torch.empty((total,), dtype=torch.uint8, device=self.device)
+        self.d_geom[:n].copy_(torch.from_numpy(g))
+        self.d_canvas_off[:n].copy_(torch.from_numpy(off[:n].copy()))
+        self._geom_host = g
+        self._offsets = off
+        self._n_images = n
+
+    # ------------------------------------------------------------------ launch
+    def enqueue(self, d_detections, d_mrcnn_mask, stream=None):
+        """Enqueue the three kernels for the planned batch on `stream` (no host sync).
+        d_detections [n,R,6] and d_mrcnn_mask [n,R,mh,mw,C] are device tensors of the
+        dtypes given at construction."""
+        n = self._n_images
+        if n == 0:
+            raise RuntimeError("call plan() first")
+        torch = _torch()
+        if tuple(d_detections.shape) != (n, self.R, 6) or \
+                d_detections.dtype != _torch_dtype(self.det_dtype):
+            raise ValueError(f"detections must be {(n, self.R, 6)} {self.det_dtype}, got "
+                             f"{tuple(d_detections.shape)} {d_detections.dtype}")
+        if tuple(d_mrcnn_mask.shape) != (n, self.R, self.mh, self.mw, self.C) or \
+                d_mrcnn_mask.dtype != _torch_dtype(self.mask_dtype):
+            raise ValueError(f"mrcnn_mask must be {(n, self.R, self.mh, self.mw, self.C)} "
+                             f"{self.mask_dtype}, got {tuple(d_mrcnn_mask.shape)} "
+                             f"{d_mrcnn_mask.dtype}")
+        if not (d_detections.is_contiguous() and d_mrcnn_mask.is_contiguous()):
+            raise ValueError("inputs must be contiguous")
+        st = N.stream_ptr(stream)
+        lib = self.lib
+        N.check(lib.mrx_unmold_prologue(
+            _ptr(d_detections), _dtype_code(self.det_dtype), n, self.R, self.C,
+            _ptr(self.d_geom), _ptr(self.d_boxes), _ptr(self.d_class_ids),
+            _ptr(self.d_scores), _ptr(self.d_src_index), _ptr(self.d_counts),
+            _ptr(self.d_status), _ptr(self.d_job_counter), st), "mrx_unmold_prologue")
+        N.check(lib.mrx_gather_tiles(
+            _ptr(d_mrcnn_mask), _dtype_code(self.mask_dtype), n, self.R, self.mh, self.mw,
+            self.C, _ptr(self.d_class_ids), _ptr(self.d_src_index), _ptr(self.d_counts),
+            _ptr(self.d_tiles), st), "mrx_gather_tiles")
+        self.enqueue_expand(stream)
+
+    def enqueue_expand(self, stream=None, reset_counter=False):
+        """Only the mask-expand kernel (boxes / tiles / counts already on the device)."""
+        n = self._n_images
+        if reset_counter:
+            self.d_job_counter.zero_()
+        N.check(self.lib.mrx_mask_expand(
+            _ptr(self.d_tiles), _ptr(self.d_boxes), _ptr(self.d_counts), _ptr(self.d_geom),
+            _ptr(self.d_canvas_off), _ptr(self.d_canvas), n, self.R, self.mh, self.mw,
+            self.chunk_bytes, self.ctas_per_sm, _ptr(self.d_job_counter),
+            N.stream_ptr(stream)), "mrx_mask_expand")
+
+    # ------------------------------------------------------------------ results
+    def canvas_bytes(self, counts):
+        """Algorithmic canvas bytes for kept counts (sum H*W*N)."""
+        g = self._geom_host
+        return int((g[:, 0].astype(np.int64) * g[:, 1] * np.asarray(counts, np.int64)).sum())
+
+    def canvas_view(self, b, n_kept):
+        """uint8 device view [H, W, n_kept] of image b's slot (values 0/1)."""
+        g = self._geom_host[b]
+        H, W = int(g[0]), int(g[1])
+        o = int(self._offsets[b])
+        return self.d_canvas[o:o + H * W * n_kept].view(H, W, n_kept)
+
+    def fetch_meta(self):
+        """Copy counts/status/boxes/class_ids/scores of the planned batch to the host
+        (synchronises the current stream). Raises like numpy would on bad inputs."""
+        n = self._n_images
+        counts = self.d_counts[:n].cpu().numpy()
+        status = self.d_status[:n].cpu().numpy()
+        if (status & N.MRX_ST_CLASS_RANGE).any():
+            b = int(np.nonzero(status & N.MRX_ST_CLASS_RANGE)[0][0])
+            raise IndexError(f"image {b}: class id out of bounds for axis 3 with size {self.C}")
+        if (status & N.MRX_ST_BOX_RANGE).any():
+            b = int(np.nonzero(status & N.MRX_ST_BOX_RANGE)[0][0])
+            raise ValueError(f"image {b}: a detection box falls outside the original image; "
+                             "the reference's mask paste cannot broadcast it")
+        boxes = self.d_boxes[:n].cpu().numpy()
+        class_ids = self.d_class_ids[:n].cpu().numpy()
+        scores = self.d_scores[:n].cpu().numpy()
+        return counts, boxes, class_ids, scores
+
+
+class AnchorGenerator:
+    """`get_anchors` on the device; memoised by image shape like upstream's method."""
+
+    def __init__(self, config, device=None):
+        N.require_cuda()
+        torch = _torch()
+        self.lib = N.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.scales = [float(s) for s in config.RPN_ANCHOR_SCALES]
+        self.ratios = [float(r) for r in config.RPN_ANCHOR_RATIOS]
+        self.strides = [int(s) for s in config.BACKBONE_STRIDES]
+        self.anchor_stride = int(config.RPN_ANCHOR_STRIDE)
+        if len(self.scales) != len(self.strides):
+            raise ValueError("RPN_ANCHOR_SCALES and BACKBONE_STRIDES must have equal length")
+        self._cache = {}
+
+    def count(self, image_shape):
+        out = C.c_longlong(0)
+        N.check(self.lib.mrx_anchor_count(
+            int(image_shape[0]), int(image_shape[1]), N.int_array(self.strides),
+            len(self.strides), len(self.ratios), self.anchor_stride, C.byref(out)),
+            "mrx_anchor_count")
+        return int(out.value)
+
+    def generate_device(self, image_shape, out=None, stream=None):
+        """[A,4] float32 device tensor (not cached)."""
+        torch = _torch()
+        A = self.count(image_shape)
+        if out is None:
+            out = torch.empty((A, 4), dtype=torch.float32, device=self.device)
+        N.check(self.lib.mrx_anchors(
+            _ptr(out), int(image_shape[0]), int(image_shape[1]),
+            N.double_array(self.scales), N.double_array(self.ratios),
+            N.int_array(self.strides), len(self.strides), len(self.ratios),
+            self.anchor_stride, N.stream_ptr(stream)), "mrx_anchors")
+        return out
+
+    def get_anchors(self, image_shape):
+        key = tuple(int(v) for v in image_shape)
+        if key not in self._cache:
+            self._cache[key] = self.generate_device(image_shape).cpu().numpy()
+        return self._cache[key]
+
+
+def resize_image_geometry(h, w, min_dim, max_dim, min_scale, mode):
+    """Host-side scalar logic of upstream utils.resize_image (serve.py:91-97): returns
+    (new_h, new_w, top, left, out_h, out_w, window, scale, padding).  `crop` mode is
+    random/training-only and not part of serving."""
+    scale = 1
+    if mode == "none":
+        return h, w, 0, 0, h, w, (0, 0, h, w), 1, [(0, 0), (0, 0), (0, 0)]
+    if min_dim:
+        scale = max(1, min_dim / min(h, w))
+    if min_scale and scale < min_scale:
+        scale = min_scale
+    if max_dim and mode == "square":
+        image_max = max(h, w)
+        if round(image_max * scale) > max_dim:
+            scale = max_dim / image_max
+    nh, nw = (round(h * scale), round(w * scale)) if scale != 1 else (h, w)
+    if mode == "square":
+        top = (max_dim - nh) // 2
+        bottom = max_dim - nh - top
+        left = (max_dim - nw) // 2
+        right = max_dim - nw - left
+        out_h, out_w = max_dim, max_dim
+    elif mode == "pad64":
+        assert min_dim % 64 == 0, "Minimum dimension must be a multiple of 64"
+        if nh % 64 > 0:
+            max_h = nh - (nh % 64) + 64
+            top = (max_h - nh) // 2
+            bottom = max_h - nh - top
+        else:
+            top = bottom = 0
+        if nw % 64 > 0:
+            max_w = nw - (nw % 64) + 64
+            left = (max_w - nw) // 2
+            right = max_w - nw - left
+        else:
+            left = right = 0
+        out_h, out_w = nh + top + bottom, nw + left + right
+    else:
+        raise Exception("Mode {} not supported".format(mode))
+    if top < 0 or left < 0:
+        raise ValueError("image larger than IMAGE_MAX_DIM after scaling")
+    padding = [(top, bottom), (left, right), (0, 0)]
+    window = (top, left, nh + top, nw + left)
+    return nh, nw, top, left, out_h, out_w, window, scale, padding
+
+
+class Molder:
+    """cv2.resize + resize_image + mold_image on the device (serve.py:88-98)."""
+
+    def __init__(self, config, device=None):
+        N.require_cuda()
+        torch = _torch()
+        self.lib = N.load()
+        self.config = config
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+
+    def cv2_resize_device(self, d_img, size_hw, stream=None):
+        torch = _torch()
+        sh, sw = int(d_img.shape[0]), int(d_img.shape[1])
+        dh, dw = int(size_hw[0]), int(size_hw[1])
+        out = torch.empty((dh, dw, 3), dtype=torch.uint8, device=self.device)
+        N.check(self.lib.mrx_cv2_resize_u8c3(_ptr(d_img), sh, sw, _ptr(out), dh, dw,
+                                             N.stream_ptr(stream)), "mrx_cv2_resize_u8c3")
+        return out
+
+    def mold_device(self, d_img, out_dtype=np.float32, want_u8=False, stream=None):
+        """resize_image + mold_image for a uint8 HxWx3 device image.
+        Returns (molded, molded_u8|None, window, scale, padding)."""
+        torch = _torch()
+        cfg = self.config
+        h, w = int(d_img.shape[0]), int(d_img.shape[1])
+        nh, nw, top, left, oh, ow, window, scale, padding = resize_image_geometry(
+            h, w, cfg.IMAGE_MIN_DIM, cfg.IMAGE_MAX_DIM, cfg.IMAGE_MIN_SCALE,
+            cfg.IMAGE_RESIZE_MODE)
+        out = torch.empty((oh, ow, 3), dtype=_torch_dtype(out_dtype), device=self.device)
+        u8 = torch.empty((oh, ow, 3), dtype=torch.uint8, device=self.device) if want_u8 \
+            else None
+        mean = [float(v) for v in np.asarray(cfg.MEAN_PIXEL, dtype=np.float64)]
+        N.check(self.lib.mrx_mold_image(
+            _ptr(d_img), h, w, nh, nw, top, left, oh, ow, N.double_array(mean),
+            _dtype_code(out_dtype), _ptr(out),
+            _ptr(u8) if u8 is not None else C.c_void_p(0), N.stream_ptr(stream)),
+            "mrx_mold_image")
+        return out, u8, window, scale, padding

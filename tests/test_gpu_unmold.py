@@ -1,0 +1,176 @@
+"""GPU parity of api_utils.unmold_detections (serve.py:147-154) against the oracle.
+
+Contract: N, boxes, class_ids, scores bit-exact; binary masks equal
+wherever the oracle's float64 pre-threshold value is > 1e-6 away from 0.5.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from matterport_maskrcnn_with_tensorflow_serving_b200 import api_utils, synth
+from matterport_maskrcnn_with_tensorflow_serving_b200.engine import UnmoldEngine, make_geom
+
+from helpers import MASK_VALUE_ATOL, compare_masks, item_of, oracle_unmold
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_image(im, dtype):
+    ref_b, ref_c, ref_s, ref_m, resized = oracle_unmold(im, dtype, return_resized=True)
+    b, c, s, m = api_utils.unmold_detections(*item_of(im, dtype))
+    assert b.dtype == np.int32 and c.dtype == np.int32
+    np.testing.assert_array_equal(b, ref_b)
+    np.testing.assert_array_equal(c, ref_c)
+    assert s.dtype == ref_s.dtype
+    np.testing.assert_array_equal(s, ref_s)
+    bad, band = compare_masks(m, ref_m, resized, ref_b)
+    assert bad == 0, f"{bad} mask pixels differ outside the +-{MASK_VALUE_ATOL} band"
+    return band
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("hw,n,classes", [
+    ((1024, 1024), 10, 81),      # BASELINE.json config 1 shape
+    ((96, 128), 12, 5),
+    ((800, 1333), 37, 81),       # COCO shape: rows not 16-byte aligned, ragged N
+    ((333, 517), 100, 2),        # tiny-class case, odd sizes
+])
+def test_unmold_matches_oracle(cuda_device, hw, n, classes, dtype):
+    im = synth.make_batch(11, 1, hw, n, num_classes=classes)[0]
+    _check_image(im, dtype)
+
+
+def test_trim_at_first_zero_class_and_zero_area(cuda_device):
+    rng = np.random.default_rng(5)
+    im = synth.make_image(rng, (200, 300), 20, num_classes=7, zero_area_rows=(0, 7, 19))
+    im.detections[15, 4] = 0.0      # early class-0 row truncates; rows 16.. ignored
+    ref = oracle_unmold(im)
+    got = api_utils.unmold_detections(*item_of(im))
+    assert got[0].shape[0] == ref[0].shape[0] == 13    # 15 rows minus zero-area rows 0 and 7
+    for g, r in zip(got[:3], ref[:3]):
+        np.testing.assert_array_equal(g, r)
+    _check_image(im, np.float64)
+
+
+def test_no_detections(cuda_device):
+    rng = np.random.default_rng(6)
+    im = synth.make_image(rng, (64, 80), 0, num_classes=3)
+    b, c, s, m = api_utils.unmold_detections(*item_of(im))
+    rb, rc, rs, rm = oracle_unmold(im)
+    assert b.shape == rb.shape == (0, 4) and c.shape == (0,) and s.shape == (0,)
+    assert m.shape == rm.shape == (64, 80, 0) and m.dtype == rm.dtype
+
+
+def test_leading_unit_batch_dim(cuda_device):
+    im = synth.make_batch(3, 1, (120, 90), 6, num_classes=4)[0]
+    it = item_of(im)
+    got = api_utils.unmold_detections(it[0][None], it[1][None], *it[2:])
+    ref = oracle_unmold(im)
+    np.testing.assert_array_equal(got[0], ref[0])
+    np.testing.assert_array_equal(got[3], ref[3])
+
+
+def test_small_boxes_downscale(cuda_device):
+    # boxes smaller than the 28x28 tile (no anti-aliasing in the reference)
+    rng = np.random.default_rng(8)
+    im = synth.make_image(rng, (150, 150), 30, num_classes=3, min_box=1, max_box_frac=0.1)
+    _check_image(im, np.float64)
+
+
+def test_batch_ragged_counts(cuda_device):
+    ims = synth.make_batch(21, 5, (240, 320), (0, 40), num_classes=6, max_instances=40)
+    got = api_utils.unmold_detections_batch([item_of(im) for im in ims])
+    for im, g in zip(ims, got):
+        rb, rc, rs, rm, rz = oracle_unmold(im, return_resized=True)
+        np.testing.assert_array_equal(g[0], rb)
+        np.testing.assert_array_equal(g[1], rc)
+        np.testing.assert_array_equal(g[2], rs)
+        if rb.shape[0]:
+            assert compare_masks(g[3], rm, rz, rb)[0] == 0
+        else:
+            assert g[3].shape == rm.shape
+
+
+@pytest.mark.parametrize("chunk", [1024, 4096, 20000 // 16 * 16, 102400])
+def test_chunk_size_independent(cuda_device, chunk):
+    """The canvas is cut into flat chunks; results must not depend on the cut."""
+    import torch
+
+    ims = synth.make_batch(31, 3, (130, 170), (5, 25), num_classes=4, max_instances=25)
+    eng = UnmoldEngine(3, 25, (28, 28), 4, chunk_bytes=chunk)
+    eng.plan([make_geom(im.original_image_shape, im.image_shape, im.window) for im in ims])
+    d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
+    d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
+    eng.enqueue(d_det, d_msk)
+    counts, boxes, cls, scores = eng.fetch_meta()
+    for b, im in enumerate(ims):
+        rb, rc, rs, rm, rz = oracle_unmold(im, np.float32, return_resized=True)
+        k = int(counts[b])
+        assert k == rb.shape[0]
+        m = eng.canvas_view(b, k).cpu().numpy().view(np.bool_)
+        assert compare_masks(m, rm, rz, rb)[0] == 0
+
+
+def test_resized_values_within_tolerance(cuda_device):
+    """Pre-threshold values: |gpu_fp32 - oracle_fp64| <= 1e-6 (stated tolerance)."""
+    import ctypes as C
+
+    import torch
+
+    from matterport_maskrcnn_with_tensorflow_serving_b200 import _native as N
+
+    lib = N.load()
+    rng = np.random.default_rng(9)
+    worst = 0.0
+    for (bh, bw) in [(28, 28), (287, 311), (5, 9), (1, 1), (512, 3), (3, 640), (1000, 777)]:
+        tile = rng.random((28, 28), dtype=np.float32)
+        d_tile = torch.from_numpy(tile).cuda()
+        d_out = torch.empty((bh, bw), dtype=torch.float32, device="cuda")
+        N.check(lib.mrx_resize_tile_f32(C.c_void_p(d_tile.data_ptr()), 28, 28, bh, bw,
+                                        C.c_void_p(d_out.data_ptr()), N.stream_ptr(None)),
+                "mrx_resize_tile_f32")
+        ref = oracle.resize(tile.astype(np.float64), (bh, bw))
+        err = np.abs(d_out.cpu().numpy().astype(np.float64) - ref).max()
+        worst = max(worst, err)
+        if (bh, bw) == (28, 28):
+            assert err == 0.0        # identity resize is exact
+    assert worst <= MASK_VALUE_ATOL, worst
+
+
+def test_bad_class_id_raises_like_numpy(cuda_device):
+    im = synth.make_batch(4, 1, (64, 64), 3, num_classes=3)[0]
+    im.detections[1, 4] = 7.0
+    with pytest.raises(IndexError):
+        oracle_unmold(im)
+    with pytest.raises(IndexError):
+        api_utils.unmold_detections(*item_of(im))
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE.json config 2 shape (1024x1024, 100 instances) on a few images: values are
+    0/1, support of instance n lies inside box n, and per-instance pixel counts equal the
+    oracle's for a sampled subset of instances."""
+    import torch
+
+    ims = synth.make_batch(77, 4, (1024, 1024), 100)
+    eng = UnmoldEngine(4, 100, (28, 28), 81)
+    eng.plan([make_geom(im.original_image_shape, im.image_shape, im.window) for im in ims])
+    d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
+    d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
+    eng.enqueue(d_det, d_msk)
+    counts, boxes, cls, scores = eng.fetch_meta()
+    for b, im in enumerate(ims):
+        k = int(counts[b])
+        assert k == 100
+        v = eng.canvas_view(b, k)
+        assert int(v.max()) <= 1
+        per_inst = v.sum(dim=(0, 1), dtype=torch.int64).cpu().numpy()
+        m = v.cpu().numpy().view(np.bool_)
+        for i in range(0, k, 9):
+            y1, x1, y2, x2 = boxes[b, i]
+            assert m[:, :, i].sum() == m[y1:y2, x1:x2, i].sum() == per_inst[i]
+            tile = im.mrcnn_mask[i, :, :, int(cls[b, i])].astype(np.float64)
+            rz = oracle.resize(tile, (y2 - y1, x2 - x1))
+            ref = rz >= 0.5
+            d = m[y1:y2, x1:x2, i] != ref
+            assert not (d & (np.abs(rz - 0.5) > MASK_VALUE_ATOL)).any()
