@@ -178,25 +178,42 @@ gather_tiles_kernel(const T *__restrict__ mask, int R, int tile_elems, int C,
 // A job is `chunk_bytes` consecutive bytes of one image's [H,W,N] canvas (flat byte
 // stream; N innermost so a pixel is N consecutive bytes).  Per job the CTA
 //   1. lists the (box, row) pairs that intersect the chunk            -> entries
+//      (lane-parallel: one thread per pair does all per-entry scalar math once)
 //   2. stages the two tile rows each entry interpolates between with a 1-D TMA bulk
 //      copy (224 B at mw = 28) and blends them vertically in place
-//   3. walks each entry's x-span: exact integer source coordinate, fp32 lerp of the
-//      blended row, >= 0.5, byte store into the shared-memory chunk
+//   3. walks each entry's x-span: exact integer source coordinate (incremental along
+//      the span), fp32 lerp of the blended row, >= 0.5, byte store into the shared chunk
 //   4. hands the chunk to the TMA with one bulk store (HBM sees one write per byte)
-// Zero fill is the memset of the shared chunk, skipped when the previous job left it
-// all-zero.
+// Zero fill is the memset of the shared chunk, skipped for the part already known zero.
+// Job descriptors are computed by one thread a job ahead (double-buffered in smem) so
+// the 32-bit divisions are off the critical path of the other warps.
 constexpr int kExpandThreads = 256;
 constexpr int kExpandWarps = kExpandThreads / 32;
-constexpr int kEMax = 128;  // entries per pass == pairs tested per pass
+constexpr int kEMax = 64;  // entries per pass == pairs tested per pass
 
 struct __align__(16) Entry {
-  int n;       // instance index (position along the innermost canvas axis)
-  int row;     // canvas row
-  int xa, xb;  // span [xa, xb) of canvas columns inside the chunk and the box
-  int x1;      // box left
-  int bw;      // box width
-  int j0;      // floor of the source row coordinate, in [-1, mh-1]
-  float wy;    // its fractional part
+  int obase;    // byte offset of (row, x=0, n) relative to the chunk start
+  int xa, xb;   // span [xa, xb) of canvas columns inside the chunk and the box
+  int x1;       // box left
+  int D;        // 2 * box width
+  float invD;   // 1 / D
+  int stepQ;    // (64*mw) / D : source-column advance per 32 canvas columns
+  int stepR;    // (64*mw) % D
+  float wy;     // vertical weight of the lower source row
+  int otop;     // float offset of the upper source row inside the staging slot, -1 = outside
+  int obot;     // same for the lower source row
+  int pad_;
+};
+
+struct __align__(16) JobInfo {
+  const float *tiles_b;
+  const int4 *boxes_b;
+  unsigned char *dst;
+  int valid;
+  int H, W, N;
+  int len, len16;
+  int g0, g1, r0, n_pairs, sub;
+  int pad_;
 };
 
 struct ExpandParams {
@@ -209,6 +226,40 @@ struct ExpandParams {
   unsigned int *job_counter;
   int B, R, mh, mw, chunk_bytes;
 };
+
+__device__ __forceinline__ void make_job(const ExpandParams &p, const int *s_jobs, int total_jobs,
+                                         int job, int &cur_b, JobInfo *out) {
+  if (job >= total_jobs) {
+    out->valid = 0;
+    return;
+  }
+  while (job >= s_jobs[cur_b + 1]) ++cur_b;
+  const int b = cur_b;
+  const int H = p.geom[b * MRX_GEOM_INTS + 0];
+  const int W = p.geom[b * MRX_GEOM_INTS + 1];
+  const int N = p.counts[b];
+  const unsigned L = static_cast<unsigned>(H) * W * N;         // host guarantees < 2^31
+  const unsigned c0 = static_cast<unsigned>(job - s_jobs[b]) * p.chunk_bytes;
+  const int len = static_cast<int>(min(static_cast<unsigned>(p.chunk_bytes), L - c0));
+  const int g0 = static_cast<int>(c0 / N);               // first pixel touched
+  const int g1 = static_cast<int>((c0 + len - 1) / N);   // last pixel touched
+  const int r0 = g0 / W;
+  const int r1 = g1 / W;
+  out->tiles_b = p.tiles + static_cast<size_t>(b) * p.R * p.mh * p.mw;
+  out->boxes_b = p.boxes + static_cast<size_t>(b) * p.R;
+  out->dst = p.canvas + p.canvas_off[b] + c0;
+  out->H = H;
+  out->W = W;
+  out->N = N;
+  out->len = len;
+  out->len16 = (len + 15) & ~15;
+  out->g0 = g0;
+  out->g1 = g1;
+  out->r0 = r0;
+  out->n_pairs = (r1 - r0 + 1) * N;
+  out->sub = static_cast<int>(c0 - static_cast<unsigned>(g0) * N);   // bytes of pixel g0 before c0
+  out->valid = 1;
+}
 
 __global__ void __launch_bounds__(kExpandThreads)
 mask_expand_kernel(const ExpandParams p) {
@@ -225,10 +276,11 @@ mask_expand_kernel(const ExpandParams p) {
   float *s_stage = reinterpret_cast<float *>(smem + p.chunk_bytes);   // kEMax slots
   Entry *s_entry = reinterpret_cast<Entry *>(s_stage + kEMax * slot_floats);
   int *s_jobs = reinterpret_cast<int *>(s_entry + kEMax);             // B + 1 prefix
+  __shared__ JobInfo s_job[2];
   __shared__ uint64_t s_bar;
   __shared__ int s_count[2];
-  __shared__ int s_jobid;
-  __shared__ int s_carry;
+  __shared__ int s_next;
+  __shared__ int s_total;
 
   // ---- job table: jobs_b = ceil(H*W*N_b / chunk); exclusive prefix in s_jobs
   if (warp == 0) {
@@ -252,7 +304,7 @@ mask_expand_kernel(const ExpandParams p) {
     }
     if (lane == 0) {
       s_jobs[0] = 0;
-      s_carry = carry;
+      s_total = carry;
     }
   }
   if (tid == 0) {
@@ -262,85 +314,76 @@ mask_expand_kernel(const ExpandParams p) {
     s_count[1] = 0;
   }
   __syncthreads();
-  const int total_jobs = s_carry;
+  const int total_jobs = s_total;
 
+  const uint32_t s_out_addr = smem_u32(s_out);
   uint32_t bar_parity = 0;
   int pass_parity = 0;
-  int cur_b = 0;
-  bool dirty = true;          // shared chunk not known to be all-zero yet
-  int next_job = 0;
-  if (tid == 0) next_job = static_cast<int>(atomicAdd(p.job_counter, 1u));
+  int cur_b = 0;       // thread 0 only: image of the most recently described job
+  int next_job = 0;    // thread 0 only
+  int clean = 0;       // bytes [0, clean) of s_out known to be zero
+  if (tid == 0) {
+    const int j = static_cast<int>(atomicAdd(p.job_counter, 1u));
+    make_job(p, s_jobs, total_jobs, j, cur_b, &s_job[0]);
+    next_job = static_cast<int>(atomicAdd(p.job_counter, 1u));
+  }
 
-  while (true) {
-    if (tid == 0) {
-      s_jobid = next_job;
-      bulk_wait_read<0>();    // the previous chunk has left shared memory
-    }
-    __syncthreads();          // (S1) job id visible, s_out reusable, staging reusable
-    const int job = s_jobid;
-    if (job >= total_jobs) break;
-    if (tid == 0) next_job = static_cast<int>(atomicAdd(p.job_counter, 1u));
+  for (int k = 0;; ++k) {
+    if (tid == 0) bulk_wait_read<0>();   // the previous chunk has left shared memory
+    __syncthreads();   // (S1) job descriptor visible, s_out and staging reusable
+    const JobInfo J = s_job[k & 1];
+    if (!J.valid) break;
 
-    while (job >= s_jobs[cur_b + 1]) ++cur_b;
-    const int b = cur_b;
-    const int H = p.geom[b * MRX_GEOM_INTS + 0];
-    const int W = p.geom[b * MRX_GEOM_INTS + 1];
-    const int N = p.counts[b];
-    const long long L = static_cast<long long>(H) * W * N;
-    const long long c0 = static_cast<long long>(job - s_jobs[b]) * p.chunk_bytes;
-    const int len = static_cast<int>(min(static_cast<long long>(p.chunk_bytes), L - c0));
-    const int len16 = (len + 15) & ~15;
-    const int g0 = static_cast<int>(c0 / N);                 // first pixel touched
-    const int g1 = static_cast<int>((c0 + len - 1) / N);     // last pixel touched
-    const int r0 = g0 / W;
-    const int r1 = g1 / W;
-    const int n_pairs = (r1 - r0 + 1) * N;
-    const int sub = static_cast<int>(c0 - static_cast<long long>(g0) * N);  // bytes of pixel g0 before c0
-    const float *tiles_b = p.tiles + static_cast<size_t>(b) * p.R * mh * mw;
-    const int4 *boxes_b = p.boxes + static_cast<size_t>(b) * p.R;
-
-    // ---- zero fill (memset of the shared chunk)
-    if (dirty) {
+    // ---- zero fill (memset of the part of the shared chunk not known to be zero)
+    if (clean < J.len16) {
       uint4 *o4 = reinterpret_cast<uint4 *>(s_out);
-      const int n16 = len16 >> 4;
-      for (int i = tid; i < n16; i += kExpandThreads) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+      const int n16 = J.len16 >> 4;
+      for (int i = (clean >> 4) + tid; i < n16; i += kExpandThreads)
+        o4[i] = make_uint4(0u, 0u, 0u, 0u);
+      clean = J.len16;
     }
     bool wrote = false;
 
-    for (int p0 = 0; p0 < n_pairs; p0 += kEMax) {
+    for (int p0 = 0; p0 < J.n_pairs; p0 += kEMax) {
       if (p0 > 0) {
         fence_proxy_async_smem();   // generic accesses to staging before the next TMA fill
         __syncthreads();
       }
-      // ---- 1. entries: thread t tests pair p0 + t
+      // ---- 1. entries: thread t tests pair p0 + t and does the per-entry scalar math
       if (tid < kEMax) {
         const int pr = p0 + tid;
         bool valid = false;
         Entry e;
-        if (pr < n_pairs) {
-          const int dr = pr / N;
-          const int n = pr - dr * N;
-          const int row = r0 + dr;
-          const int4 bx = __ldg(boxes_b + n);   // (y1, x1, y2, x2)
-          const int xlo = max(0, g0 - row * W);
-          const int xhi = min(W, g1 + 1 - row * W);
+        int jc = 0, n = 0;
+        if (pr < J.n_pairs) {
+          const int dr = pr / J.N;
+          n = pr - dr * J.N;
+          const int row = J.r0 + dr;
+          const int4 bx = __ldg(J.boxes_b + n);   // (y1, x1, y2, x2)
+          const int xlo = max(0, J.g0 - row * J.W);
+          const int xhi = min(J.W, J.g1 + 1 - row * J.W);
           const int xa = max(xlo, bx.y);
           const int xb = min(xhi, bx.w);
-          const bool sane = bx.x >= 0 && bx.y >= 0 && bx.z <= H && bx.w <= W;
+          const bool sane = bx.x >= 0 && bx.y >= 0 && bx.z <= J.H && bx.w <= J.W;
           valid = sane && row >= bx.x && row < bx.z && xa < xb;
           if (valid) {
             const int bh = bx.z - bx.x;
             const int Dy = 2 * bh;
             const int Ay = mh * (2 * (row - bx.x) + 1) - bh;
-            const int j0 = floor_div(Ay, Dy);
-            e.n = n;
-            e.row = row;
+            const int j0 = floor_div(Ay, Dy);   // source row floor, in [-1, mh-1]
+            jc = min(max(j0, 0), mh - 2);       // staged rows: jc, jc+1
+            e.obase = (row * J.W - J.g0) * J.N + n - J.sub;
             e.xa = xa;
             e.xb = xb;
             e.x1 = bx.y;
-            e.bw = bx.w - bx.y;
-            e.j0 = j0;
+            e.D = 2 * (bx.w - bx.y);
+            e.invD = __fdiv_rn(1.0f, static_cast<float>(e.D));
+            e.stepQ = (64 * mw) / e.D;
+            e.stepR = (64 * mw) - e.stepQ * e.D;
             e.wy = __fdiv_rn(static_cast<float>(Ay - j0 * Dy), static_cast<float>(Dy));
+            e.otop = (j0 < 0) ? -1 : (j0 - jc) * mw;
+            e.obot = (j0 + 1 > mh - 1) ? -1 : (j0 + 1 - jc) * mw;
+            e.pad_ = 0;
           }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -350,17 +393,22 @@ mask_expand_kernel(const ExpandParams p) {
         if (valid) {
           const int slot = base + __popc(bal & ((1u << lane) - 1u));
           s_entry[slot] = e;
-          // ---- 2a. stage rows jc, jc+1 of the tile (jc clamps j0 into [0, mh-2])
-          const int jc = min(max(e.j0, 0), mh - 2);
+          // ---- 2a. stage tile rows jc, jc+1
           bulk_g2s(s_stage + slot * slot_floats,
-                   tiles_b + (static_cast<size_t>(e.n) * mh + jc) * mw, slot_bytes, &s_bar);
+                   J.tiles_b + (static_cast<size_t>(n) * mh + jc) * mw, slot_bytes, &s_bar);
         }
       }
+      if (tid == 0) s_next = 0;
       __syncthreads();   // (S2) entries + count visible; zero fill complete
       const int E = s_count[pass_parity];
       if (tid == 0) {
         s_count[pass_parity ^ 1] = 0;
         if (E > 0) mbar_arrive_expect_tx(&s_bar, E * slot_bytes);
+        if (p0 == 0) {
+          // describe the next job while the tile rows are in flight
+          make_job(p, s_jobs, total_jobs, next_job, cur_b, &s_job[(k + 1) & 1]);
+          next_job = static_cast<int>(atomicAdd(p.job_counter, 1u));
+        }
       }
       pass_parity ^= 1;
       if (E == 0) continue;
@@ -368,25 +416,25 @@ mask_expand_kernel(const ExpandParams p) {
       mbar_wait(&s_bar, bar_parity);
       bar_parity ^= 1;
 
-      // ---- 2b + 3. one warp per entry: vertical blend in place, then the x-span
-      for (int ei = warp; ei < E; ei += kExpandWarps) {
+      // ---- 2b + 3. warps grab entries: vertical blend in place, then the x-span
+      while (true) {
+        int ei = 0;
+        if (lane == 0) ei = atomicAdd(&s_next, 1);
+        ei = __shfl_sync(0xffffffffu, ei, 0);
+        if (ei >= E) break;
         const Entry e = s_entry[ei];
         float *slot = s_stage + ei * slot_floats;
         {
-          const int jc = min(max(e.j0, 0), mh - 2);
-          // slot rows: a = tile row jc, bq = tile row jc+1
           float v0 = 0.f, v1 = 0.f;   // lane handles columns lane and lane + 32
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int i = lane + 32 * h;
-            if (i < mw) {
-              const float a = slot[i];
-              const float bq = slot[mw + i];
-              const float top = (e.j0 < 0) ? 0.f : ((e.j0 == jc) ? a : bq);
-              const float bot = (e.j0 + 1 > mh - 1) ? 0.f : ((e.j0 + 1 == jc) ? a : bq);
-              const float v = fmaf(e.wy, bot - top, top);
-              if (h == 0) v0 = v; else v1 = v;
-            }
+          if (lane < mw) {
+            const float top = (e.otop >= 0) ? slot[e.otop + lane] : 0.f;
+            const float bot = (e.obot >= 0) ? slot[e.obot + lane] : 0.f;
+            v0 = fmaf(e.wy, bot - top, top);
+          }
+          if (lane + 32 < mw) {
+            const float top = (e.otop >= 0) ? slot[e.otop + lane + 32] : 0.f;
+            const float bot = (e.obot >= 0) ? slot[e.obot + lane + 32] : 0.f;
+            v1 = fmaf(e.wy, bot - top, top);
           }
           __syncwarp();
           // blended row with a zero on each side: slot[0] = 0, slot[1+i] = v_i, slot[mw+1] = 0
@@ -398,17 +446,43 @@ mask_expand_kernel(const ExpandParams p) {
           }
           __syncwarp();
         }
-        const float inv_2bw = __fdiv_rn(1.0f, static_cast<float>(2 * e.bw));
-        // byte offset of (row, x, n) inside the chunk = obase + x * N
-        const int obase = (e.row * W - g0) * N + e.n - sub;
-        for (int x = e.xa + lane; x < e.xb; x += 32) {
-          const SrcCoord sc = src_coord(x - e.x1, mw, e.bw, inv_2bw);
-          const float a = slot[sc.i0 + 1];
-          const float bq = slot[sc.i0 + 2];
-          const float v = fmaf(sc.w, bq - a, a);
-          const int off = obase + x * N;
-          if (v >= 0.5f && static_cast<unsigned>(off) < static_cast<unsigned>(len))
-            s_out[off] = 1;
+        int x = e.xa + lane;
+        if (x < e.xb) {
+          // exact start coordinate for this lane, then advance by 32 columns per step
+          int i0, rem;
+          {
+            const int A = mw * (2 * (x - e.x1) + 1) - (e.D >> 1);
+            i0 = __float2int_rd(static_cast<float>(A) * e.invD);
+            rem = A - i0 * e.D;
+            if (rem < 0) {
+              --i0;
+              rem += e.D;
+            } else if (rem >= e.D) {
+              ++i0;
+              rem -= e.D;
+            }
+          }
+          const float *rp = slot + 1 + i0;
+          unsigned off = static_cast<unsigned>(e.obase + x * J.N);
+          const unsigned ulen = static_cast<unsigned>(J.len);
+          const unsigned ostep = 32u * J.N;
+          while (true) {
+            const float wx = static_cast<float>(rem) * e.invD;
+            const float a = rp[0];
+            const float bq = rp[1];
+            const float v = fmaf(wx, bq - a, a);
+            if (v >= 0.5f && off < ulen)
+              asm volatile("st.shared.u8 [%0], %1;" ::"r"(s_out_addr + off), "r"(1u) : "memory");
+            x += 32;
+            if (x >= e.xb) break;
+            off += ostep;
+            rem += e.stepR;
+            rp += e.stepQ;
+            if (rem >= e.D) {
+              rem -= e.D;
+              ++rp;
+            }
+          }
         }
       }
     }
@@ -417,10 +491,10 @@ mask_expand_kernel(const ExpandParams p) {
     fence_proxy_async_smem();
     __syncthreads();   // (S3)
     if (tid == 0) {
-      bulk_s2g(p.canvas + p.canvas_off[b] + c0, s_out, static_cast<uint32_t>(len16));
+      bulk_s2g(J.dst, s_out, static_cast<uint32_t>(J.len16));
       bulk_commit();
     }
-    dirty = wrote;
+    if (wrote) clean = 0;
   }
   if (tid == 0) bulk_wait_all<0>();
 }
@@ -533,7 +607,7 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   MRX_CHECK_ARG(B >= 0 && B <= MRX_MAX_BATCH && R >= 1, "mrx_mask_expand: bad sizes B=%d R=%d",
                 B, R);
   if (int rc = check_mask_dims(mh, mw)) return rc;
-  if (chunk_bytes == 0) chunk_bytes = 51200;
+  if (chunk_bytes == 0) chunk_bytes = 32768;
   MRX_CHECK_ARG(chunk_bytes >= 1024 && (chunk_bytes % 16) == 0,
                 "mrx_mask_expand: chunk_bytes %d must be a multiple of 16, >= 1024", chunk_bytes);
   if (B == 0) return MRX_OK;

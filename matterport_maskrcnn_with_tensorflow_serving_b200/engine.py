@@ -110,6 +110,8 @@ class UnmoldEngine:
             raise ValueError("image sides must be >= 2")
         if (g[:, 0].astype(np.int64) * g[:, 1] > (1 << 30)).any():
             raise ValueError("canvas larger than 2^30 pixels is not supported")
+        if (g[:, 0].astype(np.int64) * g[:, 1] * self.R >= (1 << 31) - (1 << 20)).any():
+            raise ValueError("a canvas of H*W*R >= 2^31 bytes is not supported (32-bit chunk math)")
         cap = (g[:, 0].astype(np.int64) * g[:, 1].astype(np.int64) * self.R + 255) // 256 * 256
         off = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(cap, out=off[1:])

@@ -42,7 +42,8 @@ def test_unmold_matches_oracle(cuda_device, hw, n, classes, dtype):
 
 def test_trim_at_first_zero_class_and_zero_area(cuda_device):
     rng = np.random.default_rng(5)
-    im = synth.make_image(rng, (200, 300), 20, num_classes=7, zero_area_rows=(0, 7, 19))
+    # original == molded size (scale 1) so x2 == x1 in molded pixels stays zero-width
+    im = synth.make_image(rng, (1024, 1024), 20, num_classes=7, zero_area_rows=(0, 7, 19))
     im.detections[15, 4] = 0.0      # early class-0 row truncates; rows 16.. ignored
     ref = oracle_unmold(im)
     got = api_utils.unmold_detections(*item_of(im))
