@@ -12,6 +12,9 @@
 //   boxes [B,R,4] i32   class_ids/src_index [B,R] i32   scores [B,R]   counts/status [B]
 //   tiles [B,R,mh,mw] f32 (selected class only, 3136 B per instance at 28x28)
 //   canvas: image b at canvas + canvas_off[b], bytes [H_b, W_b, N_b] (N innermost)
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace mrx {
@@ -202,7 +205,7 @@ struct __align__(16) Entry {
   float wy;     // vertical weight of the lower source row
   int otop;     // float offset of the upper source row inside the staging slot, -1 = outside
   int obot;     // same for the lower source row
-  int pad_;
+  int src_off;  // float offset of the staged rows inside this image's tiles
 };
 
 struct __align__(16) JobInfo {
@@ -225,6 +228,7 @@ struct ExpandParams {
   unsigned char *canvas;
   unsigned int *job_counter;
   int B, R, mh, mw, chunk_bytes;
+  int flags;   // dev experiments: 1 = LDG tile rows instead of TMA, 2 = STG chunk instead of TMA
 };
 
 __device__ __forceinline__ void make_job(const ExpandParams &p, const int *s_jobs, int total_jobs,
@@ -383,7 +387,7 @@ mask_expand_kernel(const ExpandParams p) {
             e.wy = __fdiv_rn(static_cast<float>(Ay - j0 * Dy), static_cast<float>(Dy));
             e.otop = (j0 < 0) ? -1 : (j0 - jc) * mw;
             e.obot = (j0 + 1 > mh - 1) ? -1 : (j0 + 1 - jc) * mw;
-            e.pad_ = 0;
+            e.src_off = (n * mh + jc) * mw;
           }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -394,8 +398,9 @@ mask_expand_kernel(const ExpandParams p) {
           const int slot = base + __popc(bal & ((1u << lane) - 1u));
           s_entry[slot] = e;
           // ---- 2a. stage tile rows jc, jc+1
-          bulk_g2s(s_stage + slot * slot_floats,
-                   J.tiles_b + (static_cast<size_t>(n) * mh + jc) * mw, slot_bytes, &s_bar);
+          if (!(p.flags & 1))
+            bulk_g2s(s_stage + slot * slot_floats,
+                     J.tiles_b + (static_cast<size_t>(n) * mh + jc) * mw, slot_bytes, &s_bar);
         }
       }
       if (tid == 0) s_next = 0;
@@ -403,7 +408,7 @@ mask_expand_kernel(const ExpandParams p) {
       const int E = s_count[pass_parity];
       if (tid == 0) {
         s_count[pass_parity ^ 1] = 0;
-        if (E > 0) mbar_arrive_expect_tx(&s_bar, E * slot_bytes);
+        if (E > 0 && !(p.flags & 1)) mbar_arrive_expect_tx(&s_bar, E * slot_bytes);
         if (p0 == 0) {
           // describe the next job while the tile rows are in flight
           make_job(p, s_jobs, total_jobs, next_job, cur_b, &s_job[(k + 1) & 1]);
@@ -413,8 +418,17 @@ mask_expand_kernel(const ExpandParams p) {
       pass_parity ^= 1;
       if (E == 0) continue;
       wrote = true;
-      mbar_wait(&s_bar, bar_parity);
-      bar_parity ^= 1;
+      if (!(p.flags & 1)) {
+        mbar_wait(&s_bar, bar_parity);
+        bar_parity ^= 1;
+      } else {
+        for (int ei = warp; ei < E; ei += kExpandWarps) {
+          const int so = s_entry[ei].src_off;
+          for (int i = lane; i < slot_floats; i += 32)
+            s_stage[ei * slot_floats + i] = __ldg(J.tiles_b + so + i);
+        }
+        __syncthreads();
+      }
 
       // ---- 2b + 3. warps grab entries: vertical blend in place, then the x-span
       while (true) {
@@ -490,13 +504,608 @@ mask_expand_kernel(const ExpandParams p) {
     // ---- 4. hand the chunk to the TMA
     fence_proxy_async_smem();
     __syncthreads();   // (S3)
-    if (tid == 0) {
-      bulk_s2g(J.dst, s_out, static_cast<uint32_t>(J.len16));
-      bulk_commit();
+    if (!(p.flags & 2)) {
+      if (tid == 0) {
+        bulk_s2g(J.dst, s_out, static_cast<uint32_t>(J.len16));
+        bulk_commit();
+      }
+    } else {
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out);
+      uint4 *d4 = reinterpret_cast<uint4 *>(J.dst);
+      const int n16 = J.len16 >> 4;
+      for (int i = tid; i < n16; i += kExpandThreads) __stcs(d4 + i, s4[i]);
     }
     if (wrote) clean = 0;
   }
   if (tid == 0) bulk_wait_all<0>();
+}
+
+// =====================================================================================
+// mask expand, warp-specialised: ONE persistent CTA per SM, 32 warps
+// =====================================================================================
+//
+//   warp 0      producer : fetches work units, lists the (box,row) entries of each chunk,
+//                          issues the 1-D TMA loads of their tile rows, cuts spans into units
+//   warp 1      store    : when a chunk is complete, one bulk (TMA) store shared -> HBM
+//   warps 2..31 consumers: zero fill, vertical blend, span sampling into the shared chunk
+//
+// Rings in shared memory, all hand-offs through mbarriers (no __syncthreads in steady state):
+//   item stages  (kNS): staging rows + entries + units + header     full[s] / empty[s]
+//   chunk buffers(kNB): the bytes of one job                        done[b] / free[b]
+// A job is one chunk of a canvas; an item is one pass over <= kEMax entries and <= kUMax
+// span units of a job (first item zero-fills the chunk, last item releases it to the store
+// warp).
+//
+// Work units handed out by the global counter:
+//   strip mode (row bytes W*N a multiple of 16): a unit is kBandRows consecutive rows of one
+//     row segment.  The boxes that can touch the segment are listed once per unit (active
+//     list, spans clipped once); per row only the vertical coordinate changes.
+//   flat mode (any shape): a unit is kFlatGroup consecutive flat chunks; every chunk tests
+//     all (row, box) pairs.  Chunks may start mid-pixel and span rows.
+constexpr int kWsThreads = 1024;
+constexpr int kWsWarps = kWsThreads / 32;
+constexpr int kWsConsumerWarps = kWsWarps - 2;
+constexpr int kWsConsumerThreads = kWsConsumerWarps * 32;
+constexpr int kNB = 3;
+constexpr int kNS = 2;
+constexpr int kUMax = 512;
+constexpr int kMaxUnitsPerEntry = kUMax / 32;
+constexpr int kBoxCache = 256;
+constexpr int kBandRows = 32;
+constexpr int kFlatGroup = 8;
+
+struct __align__(16) WsEntry {
+  int obase;    // byte offset of (row, x=0, n) relative to the chunk start
+  int xb;       // span end (exclusive)
+  int x1;       // box left
+  int D;        // 2 * box width
+  float invD;   // 1 / D
+  int stepQ;    // (64*mw) / D
+  int stepR;    // (64*mw) % D
+  float wy;     // vertical weight of the lower source row
+  int otop;     // float offset of the upper source row inside the staging slot, -1 = outside
+  int obot;     // same for the lower source row
+  int pad0_, pad1_;
+};
+
+struct __align__(16) WsItem {
+  int valid, buf, first, last;
+  int E, U, UL, len;
+  int len16, N, pad0_, pad1_;
+};
+
+struct __align__(16) StoreRec {
+  unsigned char *dst;
+  int len16;
+  int pad_;
+};
+
+struct __align__(16) BoxAux {
+  int D;
+  float invD;
+  int stepQ, stepR;
+};
+
+struct __align__(16) ActBox {
+  int n, xa, xb, obase;
+};
+
+__device__ __forceinline__ BoxAux make_aux(const int4 bx, int mw) {
+  BoxAux a;
+  a.D = 2 * (bx.w - bx.y);
+  if (a.D <= 0) a.D = 2;   // never used: such boxes fail the validity test
+  a.invD = __fdiv_rn(1.0f, static_cast<float>(a.D));
+  a.stepQ = (64 * mw) / a.D;
+  a.stepR = (64 * mw) - a.stepQ * a.D;
+  return a;
+}
+
+__host__ __device__ constexpr size_t ws_stage_bytes(int mw) {
+  return static_cast<size_t>(kEMax) * 2 * mw * sizeof(float) + kEMax * sizeof(WsEntry) +
+         kUMax * sizeof(uint32_t) + sizeof(WsItem);
+}
+
+// number of work units of an image (see the mode description above)
+__device__ __forceinline__ int ws_units_of(int H, int W, int N, int chunk) {
+  if (N <= 0) return 0;
+  const long long RW = static_cast<long long>(W) * N;
+  if ((RW % 16) == 0 && N <= kBoxCache) {
+    const int S = static_cast<int>((RW + chunk - 1) / chunk);
+    return S * ((H + kBandRows - 1) / kBandRows);
+  }
+  const long long jobs = (RW * H + chunk - 1) / chunk;
+  return static_cast<int>((jobs + kFlatGroup - 1) / kFlatGroup);
+}
+
+__global__ void __launch_bounds__(kWsThreads, 1)
+mask_expand_ws_kernel(const ExpandParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int mh = p.mh, mw = p.mw;
+  const int slot_floats = 2 * mw;
+  const uint32_t slot_bytes = slot_floats * 4;
+  const int chunk = p.chunk_bytes;
+
+  // ---- carve shared memory
+  unsigned char *s_out = smem;                                   // kNB * chunk
+  unsigned char *stage_base = smem + static_cast<size_t>(kNB) * chunk;
+  const size_t stage_bytes = ws_stage_bytes(mw);
+  auto stage_rows = [&](int s) { return reinterpret_cast<float *>(stage_base + s * stage_bytes); };
+  auto stage_entries = [&](int s) {
+    return reinterpret_cast<WsEntry *>(stage_base + s * stage_bytes +
+                                       static_cast<size_t>(kEMax) * slot_bytes);
+  };
+  auto stage_units = [&](int s) {
+    return reinterpret_cast<uint32_t *>(stage_base + s * stage_bytes +
+                                        static_cast<size_t>(kEMax) * slot_bytes +
+                                        kEMax * sizeof(WsEntry));
+  };
+  auto stage_item = [&](int s) {
+    return reinterpret_cast<WsItem *>(stage_base + s * stage_bytes +
+                                      static_cast<size_t>(kEMax) * slot_bytes +
+                                      kEMax * sizeof(WsEntry) + kUMax * sizeof(uint32_t));
+  };
+  unsigned char *after = stage_base + kNS * stage_bytes;
+  int4 *s_box = reinterpret_cast<int4 *>(after);
+  BoxAux *s_aux = reinterpret_cast<BoxAux *>(s_box + kBoxCache);
+  ActBox *s_act = reinterpret_cast<ActBox *>(s_aux + kBoxCache);
+  int *s_uprefix = reinterpret_cast<int *>(s_act + kBoxCache);    // B + 1 prefix of work units
+
+  __shared__ uint64_t s_full[kNS], s_empty[kNS], s_done[kNB], s_free[kNB];
+  __shared__ StoreRec s_store[kNB];
+  __shared__ int s_total;
+  __shared__ volatile int s_stop_job;
+
+  // ---- work-unit table (warp 0) and barrier init (thread 32)
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base < p.B; base += 32) {
+      const int b = base + lane;
+      int v = 0;
+      if (b < p.B)
+        v = ws_units_of(p.geom[b * MRX_GEOM_INTS + 0], p.geom[b * MRX_GEOM_INTS + 1], p.counts[b],
+                        chunk);
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (b < p.B) s_uprefix[b + 1] = carry + incl;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      s_uprefix[0] = 0;
+      s_total = carry;
+    }
+  }
+  if (tid == 32) {
+    for (int s = 0; s < kNS; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], kWsConsumerWarps);
+    }
+    for (int b = 0; b < kNB; ++b) {
+      mbar_init(&s_done[b], kWsConsumerWarps);
+      mbar_init(&s_free[b], 1);
+    }
+    s_stop_job = -1;
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int total_units = s_total;
+
+  if (warp == 0) {
+    // ================================================================= producer
+    int item_idx = 0;   // items published so far
+    int k_local = 0;    // jobs started so far
+    int st_s = 0, st_E = 0, st_U = 0;
+    float *st_rows = nullptr;
+    WsEntry *st_entries = nullptr;
+    uint32_t *st_units = nullptr;
+
+    auto open_item = [&]() {
+      st_s = item_idx % kNS;
+      mbar_wait(&s_empty[st_s], ((item_idx / kNS) & 1) ^ 1);   // consumers are done with the stage
+      st_rows = stage_rows(st_s);
+      st_entries = stage_entries(st_s);
+      st_units = stage_units(st_s);
+      st_E = 0;
+      st_U = 0;
+    };
+    auto publish_item = [&](int buf, bool first, bool last, int UL, int len, int len16, int N) {
+      if (lane == 0) {
+        WsItem it;
+        it.valid = 1;
+        it.buf = buf;
+        it.first = first ? 1 : 0;
+        it.last = last ? 1 : 0;
+        it.E = st_E;
+        it.U = st_U;
+        it.UL = UL;
+        it.len = len;
+        it.len16 = len16;
+        it.N = N;
+        it.pad0_ = 0;
+        it.pad1_ = 0;
+        *stage_item(st_s) = it;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[st_s]);
+      ++item_idx;
+    };
+    auto begin_job = [&](unsigned char *dst, int len16) -> int {
+      const int buf = k_local % kNB;
+      mbar_wait(&s_free[buf], ((k_local / kNB) & 1) ^ 1);      // chunk buffer drained
+      if (lane == 0) {
+        s_store[buf].dst = dst;
+        s_store[buf].len16 = len16;
+      }
+      return buf;
+    };
+    // One round = up to 32 candidate (box,row) pairs, one per lane.  Returns false (warp
+    // uniformly) when the open item cannot take the round; the caller publishes and retries.
+    auto emit_round = [&](bool valid, int n, int row, int xa, int xb, int obase, const int4 bx,
+                          const BoxAux ax, int ul_shift, const float *tiles_b) -> bool {
+      const unsigned bal = __ballot_sync(0xffffffffu, valid);
+      const int ecount = __popc(bal);
+      const int nu = valid ? ((xb - xa + (32 << ul_shift) - 1) >> (5 + ul_shift)) : 0;
+      int incl = nu;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      const int utotal = __shfl_sync(0xffffffffu, incl, 31);
+      if (st_E + ecount > kEMax || st_U + utotal > kUMax) return false;
+      if (ecount > 0) {
+        if (lane == 0) mbar_expect_tx(&s_full[st_s], ecount * slot_bytes);
+        __syncwarp();
+        if (valid) {
+          const int slot = st_E + __popc(bal & ((1u << lane) - 1u));
+          const int bh = bx.z - bx.x;
+          const int Dy = 2 * bh;
+          const int Ay = mh * (2 * (row - bx.x) + 1) - bh;
+          // j0 = floor(Ay / Dy) in [-1, mh-1]: float estimate + exact integer correction
+          int j0 = __float2int_rd(static_cast<float>(Ay) * __frcp_rn(static_cast<float>(Dy)));
+          int remy = Ay - j0 * Dy;
+          if (remy < 0) {
+            --j0;
+            remy += Dy;
+          } else if (remy >= Dy) {
+            ++j0;
+            remy -= Dy;
+          }
+          const int jc = min(max(j0, 0), mh - 2);
+          WsEntry e;
+          e.obase = obase;
+          e.xb = xb;
+          e.x1 = bx.y;
+          e.D = ax.D;
+          e.invD = ax.invD;
+          e.stepQ = ax.stepQ;
+          e.stepR = ax.stepR;
+          e.wy = __fdiv_rn(static_cast<float>(remy), static_cast<float>(Dy));
+          e.otop = (j0 < 0) ? -1 : (j0 - jc) * mw;
+          e.obot = (j0 + 1 > mh - 1) ? -1 : (j0 + 1 - jc) * mw;
+          e.pad0_ = 0;
+          e.pad1_ = 0;
+          st_entries[slot] = e;
+          bulk_g2s(st_rows + slot * slot_floats,
+                   tiles_b + (static_cast<size_t>(n) * mh + jc) * mw, slot_bytes, &s_full[st_s]);
+          uint32_t *up = st_units + st_U + (incl - nu);
+          for (int j = 0; j < nu; ++j)
+            up[j] = (static_cast<uint32_t>(slot) << 24) |
+                    static_cast<uint32_t>(xa + (j << (5 + ul_shift)));
+        }
+      }
+      st_E += ecount;
+      st_U += utotal;
+      return true;
+    };
+    // smallest shift such that a span of `span_max` columns has <= kMaxUnitsPerEntry units
+    auto unit_shift = [&](int span_max) -> int {
+      int sh = 0;
+      while ((32 << sh) * kMaxUnitsPerEntry < span_max) ++sh;
+      return sh;
+    };
+
+    int cur_b = 0, cached_b = -1;
+    int unit = 0;
+    if (lane == 0) unit = static_cast<int>(atomicAdd(p.job_counter, 1u));
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    while (unit < total_units) {
+      int next_unit = 0;
+      if (lane == 0) next_unit = static_cast<int>(atomicAdd(p.job_counter, 1u));
+      while (unit >= s_uprefix[cur_b + 1]) ++cur_b;
+      const int b = cur_b;
+      const int u_local = unit - s_uprefix[b];
+      const int H = p.geom[b * MRX_GEOM_INTS + 0];
+      const int W = p.geom[b * MRX_GEOM_INTS + 1];
+      const int N = p.counts[b];
+      const unsigned RW = static_cast<unsigned>(W) * N;
+      const unsigned L = RW * H;                                  // host guarantees < 2^31
+      const float *tiles_b = p.tiles + static_cast<size_t>(b) * p.R * mh * mw;
+      const int4 *boxes_b = p.boxes + static_cast<size_t>(b) * p.R;
+      unsigned char *canvas_b = p.canvas + p.canvas_off[b];
+      const bool cached = N <= kBoxCache;
+      if (cached && b != cached_b) {
+        for (int n = lane; n < N; n += 32) {
+          const int4 bx = __ldg(boxes_b + n);
+          s_box[n] = bx;
+          s_aux[n] = make_aux(bx, mw);
+        }
+        cached_b = b;
+        __syncwarp();
+      }
+
+      if ((RW % 16u) == 0u && cached) {
+        // ------------------------------------------------------------- strip mode
+        const int S = static_cast<int>((RW + chunk - 1) / chunk);
+        const int seg_bytes = ((static_cast<int>((RW + S - 1) / S)) + 15) & ~15;
+        const int sgm = u_local % S;
+        const int band = u_local / S;
+        const int ya = band * kBandRows;
+        const int yb = min(H, ya + kBandRows);
+        const int seg_off = sgm * seg_bytes;
+        const int seg_end = min(static_cast<int>(RW), seg_off + seg_bytes);
+        const int len = seg_end - seg_off;            // a multiple of 16 (RW and seg_off are)
+        if (len > 0) {
+          const int xlo = seg_off / N;                // first pixel touched
+          const int xhi = (seg_end - 1) / N;          // last pixel touched
+          const int sub = seg_off - xlo * N;          // bytes of pixel xlo before the segment
+          const int ul_shift = unit_shift(xhi - xlo + 1);
+          // active list: boxes whose clipped span is non-empty and whose rows meet the band
+          int n_act = 0;
+          for (int n0 = 0; n0 < N; n0 += 32) {
+            const int n = n0 + lane;
+            bool act = false;
+            int xa = 0, xb = 0;
+            if (n < N) {
+              const int4 bx = s_box[n];
+              xa = max(xlo, bx.y);
+              xb = min(xhi + 1, bx.w);
+              const bool sane = bx.x >= 0 && bx.y >= 0 && bx.z <= H && bx.w <= W;
+              act = sane && xa < xb && bx.x < yb && bx.z > ya && bx.z > bx.x;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, act);
+            if (act) {
+              ActBox a;
+              a.n = n;
+              a.xa = xa;
+              a.xb = xb;
+              a.obase = n - sub - xlo * N;            // (row*W - g0)*N + n - sub with g0 = row*W + xlo
+              s_act[n_act + __popc(bal & ((1u << lane) - 1u))] = a;
+            }
+            n_act += __popc(bal);
+          }
+          __syncwarp();
+          for (int y = ya; y < yb; ++y) {
+            const unsigned c0 = static_cast<unsigned>(y) * RW + seg_off;
+            const int buf = begin_job(canvas_b + c0, len);
+            open_item();
+            bool first = true;
+            for (int a0 = 0; a0 < n_act; a0 += 32) {
+              const int ai = a0 + lane;
+              bool valid = false;
+              ActBox a;
+              a.n = 0; a.xa = 0; a.xb = 0; a.obase = 0;
+              int4 bx = make_int4(0, 0, 1, 1);
+              BoxAux ax;
+              ax.D = 2; ax.invD = 0.5f; ax.stepQ = 0; ax.stepR = 0;
+              if (ai < n_act) {
+                a = s_act[ai];
+                bx = s_box[a.n];
+                ax = s_aux[a.n];
+                valid = y >= bx.x && y < bx.z;
+              }
+              while (!emit_round(valid, a.n, y, a.xa, a.xb, a.obase, bx, ax, ul_shift, tiles_b)) {
+                publish_item(buf, first, false, 32 << ul_shift, len, len, N);
+                first = false;
+                open_item();
+              }
+            }
+            publish_item(buf, first, true, 32 << ul_shift, len, len, N);
+            ++k_local;
+          }
+        }
+      } else {
+        // ------------------------------------------------------------- flat mode
+        const int jobs_b = static_cast<int>((static_cast<unsigned long long>(L) + chunk - 1) / chunk);
+        const int j_end = min(jobs_b, (u_local + 1) * kFlatGroup);
+        for (int j = u_local * kFlatGroup; j < j_end; ++j) {
+          const unsigned c0 = static_cast<unsigned>(j) * chunk;
+          const int len = static_cast<int>(min(static_cast<unsigned>(chunk), L - c0));
+          const int len16 = (len + 15) & ~15;
+          const int g0 = static_cast<int>(c0 / N);               // first pixel touched
+          const int g1 = static_cast<int>((c0 + len - 1) / N);   // last pixel touched
+          const int r0 = g0 / W;
+          const int r1 = g1 / W;
+          const int sub = static_cast<int>(c0 - static_cast<unsigned>(g0) * N);
+          const int ul_shift = unit_shift(min(W, g1 - g0 + 1));
+          const int buf = begin_job(canvas_b + c0, len16);
+          open_item();
+          bool first = true;
+          for (int row = r0; row <= r1; ++row) {
+            const int xlo = max(0, g0 - row * W);
+            const int xhi = min(W, g1 + 1 - row * W);
+            for (int n0 = 0; n0 < N; n0 += 32) {
+              const int n = n0 + lane;
+              bool valid = false;
+              int4 bx = make_int4(0, 0, 1, 1);
+              BoxAux ax;
+              ax.D = 2; ax.invD = 0.5f; ax.stepQ = 0; ax.stepR = 0;
+              int xa = 0, xb = 0;
+              if (n < N) {
+                if (cached) {
+                  bx = s_box[n];
+                  ax = s_aux[n];
+                } else {
+                  bx = __ldg(boxes_b + n);
+                  ax = make_aux(bx, mw);
+                }
+                xa = max(xlo, bx.y);
+                xb = min(xhi, bx.w);
+                const bool sane = bx.x >= 0 && bx.y >= 0 && bx.z <= H && bx.w <= W;
+                valid = sane && row >= bx.x && row < bx.z && xa < xb;
+              }
+              const int obase = (row * W - g0) * N + n - sub;
+              while (!emit_round(valid, n, row, xa, xb, obase, bx, ax, ul_shift, tiles_b)) {
+                publish_item(buf, first, false, 32 << ul_shift, len, len16, N);
+                first = false;
+                open_item();
+              }
+            }
+          }
+          publish_item(buf, first, true, 32 << ul_shift, len, len16, N);
+          ++k_local;
+        }
+      }
+      unit = __shfl_sync(0xffffffffu, next_unit, 0);
+    }
+    // sentinel item: tells consumers (and through them the store warp) to stop
+    {
+      const int s = item_idx % kNS;
+      mbar_wait(&s_empty[s], ((item_idx / kNS) & 1) ^ 1);
+      if (lane == 0) {
+        WsItem it;
+        it.valid = 0;
+        it.buf = k_local % kNB;
+        it.first = it.last = 0;
+        it.E = it.U = it.UL = it.len = it.len16 = it.N = 0;
+        it.pad0_ = it.pad1_ = 0;
+        *stage_item(s) = it;
+        s_stop_job = k_local;
+        mbar_arrive(&s_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= store warp
+    if (lane == 0) {
+      for (int k = 0;; ++k) {
+        const int b = k % kNB;
+        mbar_wait(&s_done[b], (k / kNB) & 1);
+        if (s_stop_job == k) break;
+        const StoreRec rec = s_store[b];
+        fence_proxy_async_smem();
+        bulk_s2g(rec.dst, s_out + static_cast<size_t>(b) * chunk, static_cast<uint32_t>(rec.len16));
+        bulk_commit();
+        bulk_wait_read<1>();                     // the previous chunk has left shared memory
+        if (k >= 1) mbar_arrive(&s_free[(k - 1) % kNB]);
+      }
+      bulk_wait_all<0>();
+    }
+  } else {
+    // ================================================================= consumers
+    const int cw = warp - 2;
+    const int ctid = tid - 64;
+    int clean0 = 0, clean1 = 0, clean2 = 0;   // zero prefix of each chunk buffer
+    for (int item_idx = 0;; ++item_idx) {
+      const int s = item_idx % kNS;
+      mbar_wait(&s_full[s], (item_idx / kNS) & 1);
+      const WsItem it = *stage_item(s);
+      if (!it.valid) {
+        if (lane == 0) mbar_arrive(&s_done[it.buf]);
+        break;
+      }
+      unsigned char *out = s_out + static_cast<size_t>(it.buf) * chunk;
+      const uint32_t out_addr = smem_u32(out);
+      float *rows = stage_rows(s);
+      const WsEntry *entries = stage_entries(s);
+      const uint32_t *units = stage_units(s);
+      if (it.first) {
+        int clean = (it.buf == 0) ? clean0 : ((it.buf == 1) ? clean1 : clean2);
+        if (clean < it.len16) {
+          uint4 *o4 = reinterpret_cast<uint4 *>(out);
+          const int n16 = it.len16 >> 4;
+          for (int i = (clean >> 4) + ctid; i < n16; i += kWsConsumerThreads)
+            o4[i] = make_uint4(0u, 0u, 0u, 0u);
+          clean = it.len16;
+        }
+        if (it.buf == 0) clean0 = clean; else if (it.buf == 1) clean1 = clean; else clean2 = clean;
+      }
+      // ---- vertical blend, in place: slot[0] = 0, slot[1+i] = v_i, slot[mw+1] = 0
+      for (int ei = cw; ei < it.E; ei += kWsConsumerWarps) {
+        const WsEntry e = entries[ei];
+        float *slot = rows + ei * slot_floats;
+        float v0 = 0.f, v1 = 0.f;
+        if (lane < mw) {
+          const float top = (e.otop >= 0) ? slot[e.otop + lane] : 0.f;
+          const float bot = (e.obot >= 0) ? slot[e.obot + lane] : 0.f;
+          v0 = fmaf(e.wy, bot - top, top);
+        }
+        if (lane + 32 < mw) {
+          const float top = (e.otop >= 0) ? slot[e.otop + lane + 32] : 0.f;
+          const float bot = (e.obot >= 0) ? slot[e.obot + lane + 32] : 0.f;
+          v1 = fmaf(e.wy, bot - top, top);
+        }
+        __syncwarp();
+        if (lane < mw) slot[1 + lane] = v0;
+        if (lane + 32 < mw) slot[1 + lane + 32] = v1;
+        if (lane == 0) {
+          slot[0] = 0.f;
+          slot[mw + 1] = 0.f;
+        }
+      }
+      named_bar_sync(1, kWsConsumerThreads);   // zero fill + blended rows visible to all consumers
+      // ---- span units
+      const unsigned ulen = static_cast<unsigned>(it.len);
+      const unsigned ostep = 32u * it.N;
+      for (int u = cw; u < it.U; u += kWsConsumerWarps) {
+        const uint32_t unit = units[u];
+        const int ei = static_cast<int>(unit >> 24);
+        const int x0 = static_cast<int>(unit & 0xffffffu);
+        const WsEntry e = entries[ei];
+        const float *slot = rows + ei * slot_floats;
+        const int xend = min(x0 + it.UL, e.xb);
+        int x = x0 + lane;
+        if (x < xend) {
+          int i0, rem;
+          {
+            const int A = mw * (2 * (x - e.x1) + 1) - (e.D >> 1);
+            i0 = __float2int_rd(static_cast<float>(A) * e.invD);
+            rem = A - i0 * e.D;
+            if (rem < 0) {
+              --i0;
+              rem += e.D;
+            } else if (rem >= e.D) {
+              ++i0;
+              rem -= e.D;
+            }
+          }
+          const float *rp = slot + 1 + i0;
+          unsigned off = static_cast<unsigned>(e.obase + x * it.N);
+          while (true) {
+            const float wx = static_cast<float>(rem) * e.invD;
+            const float a = rp[0];
+            const float bq = rp[1];
+            const float v = fmaf(wx, bq - a, a);
+            if (v >= 0.5f && off < ulen)
+              asm volatile("st.shared.u8 [%0], %1;" ::"r"(out_addr + off), "r"(1u) : "memory");
+            x += 32;
+            if (x >= xend) break;
+            off += ostep;
+            rem += e.stepR;
+            rp += e.stepQ;
+            if (rem >= e.D) {
+              rem -= e.D;
+              ++rp;
+            }
+          }
+        }
+      }
+      if (it.U > 0) {
+        if (it.buf == 0) clean0 = 0; else if (it.buf == 1) clean1 = 0; else clean2 = 0;
+      }
+      fence_proxy_async_smem();   // staging / chunk writes before the TMA touches them again
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[s]);
+        if (it.last) mbar_arrive(&s_done[it.buf]);
+      }
+    }
+  }
 }
 
 // =====================================================================================
@@ -607,7 +1216,7 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   MRX_CHECK_ARG(B >= 0 && B <= MRX_MAX_BATCH && R >= 1, "mrx_mask_expand: bad sizes B=%d R=%d",
                 B, R);
   if (int rc = check_mask_dims(mh, mw)) return rc;
-  if (chunk_bytes == 0) chunk_bytes = 32768;
+  if (chunk_bytes == 0) chunk_bytes = 51200;
   MRX_CHECK_ARG(chunk_bytes >= 1024 && (chunk_bytes % 16) == 0,
                 "mrx_mask_expand: chunk_bytes %d must be a multiple of 16, >= 1024", chunk_bytes);
   if (B == 0) return MRX_OK;
@@ -618,6 +1227,42 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   MRX_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 
+  ExpandParams prm;
+  prm.tiles = d_tiles;
+  prm.boxes = reinterpret_cast<const int4 *>(d_boxes);
+  prm.counts = d_counts;
+  prm.geom = d_geom;
+  prm.canvas_off = d_canvas_off;
+  prm.canvas = d_canvas;
+  prm.job_counter = d_job_counter;
+  prm.B = B;
+  prm.R = R;
+  prm.mh = mh;
+  prm.mw = mw;
+  prm.chunk_bytes = chunk_bytes;
+  {
+    const char *f = getenv("MRX_EXPAND_FLAGS");
+    prm.flags = f ? atoi(f) : 0;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char *impl = getenv("MRX_EXPAND_IMPL");
+  const bool use_v2 = impl != nullptr && strcmp(impl, "v2") == 0;
+  if (!use_v2) {
+    // warp-specialised kernel: one persistent CTA per SM
+    const size_t smem = static_cast<size_t>(kNB) * chunk_bytes + kNS * ws_stage_bytes(mw) +
+                        static_cast<size_t>(kBoxCache) * (sizeof(int4) + sizeof(BoxAux) + sizeof(ActBox)) +
+                        static_cast<size_t>(B + 1) * sizeof(int);
+    MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(max_optin),
+                        "mrx_mask_expand: %zu B shared memory > device limit %d (chunk_bytes too "
+                        "large)",
+                        smem, max_optin);
+    MRX_CUDA(cudaFuncSetAttribute(mask_expand_ws_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    mask_expand_ws_kernel<<<sms, kWsThreads, smem, st>>>(prm);
+    MRX_LAUNCH_CHECK("mask_expand_ws_kernel");
+    return MRX_OK;
+  }
   const size_t smem = static_cast<size_t>(chunk_bytes) +
                       static_cast<size_t>(kEMax) * 2 * mw * sizeof(float) +
                       static_cast<size_t>(kEMax) * sizeof(Entry) +
@@ -633,21 +1278,6 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
                                                          kExpandThreads, smem));
   MRX_CHECK_SUPPORTED(occ >= 1, "mrx_mask_expand: kernel does not fit on an SM");
   if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
-
-  ExpandParams prm;
-  prm.tiles = d_tiles;
-  prm.boxes = reinterpret_cast<const int4 *>(d_boxes);
-  prm.counts = d_counts;
-  prm.geom = d_geom;
-  prm.canvas_off = d_canvas_off;
-  prm.canvas = d_canvas;
-  prm.job_counter = d_job_counter;
-  prm.B = B;
-  prm.R = R;
-  prm.mh = mh;
-  prm.mw = mw;
-  prm.chunk_bytes = chunk_bytes;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   mask_expand_kernel<<<sms * occ, kExpandThreads, smem, st>>>(prm);
   MRX_LAUNCH_CHECK("mask_expand_kernel");
   return MRX_OK;

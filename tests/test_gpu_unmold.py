@@ -92,7 +92,7 @@ def test_batch_ragged_counts(cuda_device):
             assert g[3].shape == rm.shape
 
 
-@pytest.mark.parametrize("chunk", [1024, 4096, 20000 // 16 * 16, 102400])
+@pytest.mark.parametrize("chunk", [1024, 4096, 20000 // 16 * 16, 51200])
 def test_chunk_size_independent(cuda_device, chunk):
     """The canvas is cut into flat chunks; results must not depend on the cut."""
     import torch
