@@ -524,10 +524,10 @@ mask_expand_kernel(const ExpandParams p) {
 // mask expand, warp-specialised: ONE persistent CTA per SM, 32 warps
 // =====================================================================================
 //
-//   warp 0      producer : fetches work units, lists the (box,row) entries of each chunk,
+//   warps 30,31 producers: fetch work units, lists the (box,row) entries of each chunk,
 //                          issues the 1-D TMA loads of their tile rows, cuts spans into units
-//   warp 1      store    : when a chunk is complete, one bulk (TMA) store shared -> HBM
-//   warps 2..31 consumers: zero fill, vertical blend, span sampling into the shared chunk
+//   warp 29     store    : when a chunk is complete, one bulk (TMA) store shared -> HBM
+//   warps 0..28 consumers: zero fill, vertical blend, span sampling into the shared chunk
 //
 // Rings in shared memory, all hand-offs through mbarriers (no __syncthreads in steady state):
 //   item stages  (kNS): staging rows + entries + units + header     full[s] / empty[s]
@@ -544,15 +544,20 @@ mask_expand_kernel(const ExpandParams p) {
 //     all (row, box) pairs.  Chunks may start mid-pixel and span rows.
 constexpr int kWsThreads = 1024;
 constexpr int kWsWarps = kWsThreads / 32;
-constexpr int kWsConsumerWarps = kWsWarps - 2;
+constexpr int kProducers = 2;                       // producer warps (highest warp ids)
+constexpr int kWsConsumerWarps = kWsWarps - kProducers - 1;
 constexpr int kWsConsumerThreads = kWsConsumerWarps * 32;
-constexpr int kNB = 3;
-constexpr int kNS = 2;
+constexpr int kMaxNB = 6;   // chunk buffers: template parameter kNB in [2, kMaxNB]
+constexpr int kNS = 3;
 constexpr int kUMax = 512;
 constexpr int kMaxUnitsPerEntry = kUMax / 32;
-constexpr int kBoxCache = 256;
+constexpr int kBoxCache = 128;   // per-producer box / aux / active tables
 constexpr int kBandRows = 32;
 constexpr int kFlatGroup = 8;
+constexpr int kMinUnitShift = 2;   // span units are at least 128 columns (4 sampling steps)
+constexpr int kFirstProducerWarp = kWsWarps - kProducers;   // highest warp ids: favoured by the issue arbiter
+constexpr int kStoreWarp = kFirstProducerWarp - 1;
+static_assert(kNS >= kProducers + 1, "need a free stage beyond the ones being built");
 
 struct __align__(16) WsEntry {
   int obase;    // byte offset of (row, x=0, n) relative to the chunk start
@@ -617,6 +622,7 @@ __device__ __forceinline__ int ws_units_of(int H, int W, int N, int chunk) {
   return static_cast<int>((jobs + kFlatGroup - 1) / kFlatGroup);
 }
 
+template <int kNB>
 __global__ void __launch_bounds__(kWsThreads, 1)
 mask_expand_ws_kernel(const ExpandParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -648,18 +654,21 @@ mask_expand_ws_kernel(const ExpandParams p) {
                                       kEMax * sizeof(WsEntry) + kUMax * sizeof(uint32_t));
   };
   unsigned char *after = stage_base + kNS * stage_bytes;
-  int4 *s_box = reinterpret_cast<int4 *>(after);
+  constexpr size_t kTableBytes = kBoxCache * (sizeof(int4) + sizeof(BoxAux) + sizeof(ActBox));
+  const int prod = (warp >= kFirstProducerWarp) ? warp - kFirstProducerWarp : 0;
+  int4 *s_box = reinterpret_cast<int4 *>(after + prod * kTableBytes);   // producer-private
   BoxAux *s_aux = reinterpret_cast<BoxAux *>(s_box + kBoxCache);
   ActBox *s_act = reinterpret_cast<ActBox *>(s_aux + kBoxCache);
-  int *s_uprefix = reinterpret_cast<int *>(s_act + kBoxCache);    // B + 1 prefix of work units
+  int *s_uprefix = reinterpret_cast<int *>(after + kProducers * kTableBytes);   // B + 1 prefix
 
   __shared__ uint64_t s_full[kNS], s_empty[kNS], s_done[kNB], s_free[kNB];
   __shared__ StoreRec s_store[kNB];
   __shared__ int s_total;
   __shared__ volatile int s_stop_job;
+  __shared__ int s_item_ticket, s_job_ticket, s_fin_count;
 
-  // ---- work-unit table (warp 0) and barrier init (thread 32)
-  if (warp == 0) {
+  // ---- work-unit table (first producer warp) and barrier init (store warp)
+  if (warp == kFirstProducerWarp) {
     int carry = 0;
     for (int base = 0; base < p.B; base += 32) {
       const int b = base + lane;
@@ -681,7 +690,7 @@ mask_expand_ws_kernel(const ExpandParams p) {
       s_total = carry;
     }
   }
-  if (tid == 32) {
+  if (warp == kStoreWarp && lane == 0) {
     for (int s = 0; s < kNS; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], kWsConsumerWarps);
@@ -691,21 +700,28 @@ mask_expand_ws_kernel(const ExpandParams p) {
       mbar_init(&s_free[b], 1);
     }
     s_stop_job = -1;
+    s_item_ticket = 0;
+    s_job_ticket = 0;
+    s_fin_count = 0;
     fence_mbar_init();
   }
   __syncthreads();
   const int total_units = s_total;
 
-  if (warp == 0) {
-    // ================================================================= producer
-    int item_idx = 0;   // items published so far
-    int k_local = 0;    // jobs started so far
+  if (warp >= kFirstProducerWarp) {
+    // ================================================================= producers
+    // Items and jobs are numbered by CTA-wide tickets so that several producer warps can
+    // build different items concurrently; consumers take items, the store warp takes jobs,
+    // in ticket order.
     int st_s = 0, st_E = 0, st_U = 0;
     float *st_rows = nullptr;
     WsEntry *st_entries = nullptr;
     uint32_t *st_units = nullptr;
 
     auto open_item = [&]() {
+      int item_idx = 0;
+      if (lane == 0) item_idx = atomicAdd(&s_item_ticket, 1);
+      item_idx = __shfl_sync(0xffffffffu, item_idx, 0);
       st_s = item_idx % kNS;
       mbar_wait(&s_empty[st_s], ((item_idx / kNS) & 1) ^ 1);   // consumers are done with the stage
       st_rows = stage_rows(st_s);
@@ -733,11 +749,13 @@ mask_expand_ws_kernel(const ExpandParams p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_full[st_s]);
-      ++item_idx;
     };
     auto begin_job = [&](unsigned char *dst, int len16) -> int {
-      const int buf = k_local % kNB;
-      mbar_wait(&s_free[buf], ((k_local / kNB) & 1) ^ 1);      // chunk buffer drained
+      int q = 0;
+      if (lane == 0) q = atomicAdd(&s_job_ticket, 1);
+      q = __shfl_sync(0xffffffffu, q, 0);
+      const int buf = q % kNB;
+      mbar_wait(&s_free[buf], ((q / kNB) & 1) ^ 1);            // chunk buffer drained
       if (lane == 0) {
         s_store[buf].dst = dst;
         s_store[buf].len16 = len16;
@@ -806,7 +824,7 @@ mask_expand_ws_kernel(const ExpandParams p) {
     };
     // smallest shift such that a span of `span_max` columns has <= kMaxUnitsPerEntry units
     auto unit_shift = [&](int span_max) -> int {
-      int sh = 0;
+      int sh = kMinUnitShift;
       while ((32 << sh) * kMaxUnitsPerEntry < span_max) ++sh;
       return sh;
     };
@@ -907,7 +925,6 @@ mask_expand_ws_kernel(const ExpandParams p) {
               }
             }
             publish_item(buf, first, true, 32 << ul_shift, len, len, N);
-            ++k_local;
           }
         }
       } else {
@@ -959,28 +976,31 @@ mask_expand_ws_kernel(const ExpandParams p) {
             }
           }
           publish_item(buf, first, true, 32 << ul_shift, len, len16, N);
-          ++k_local;
         }
       }
       unit = __shfl_sync(0xffffffffu, next_unit, 0);
     }
-    // sentinel item: tells consumers (and through them the store warp) to stop
-    {
-      const int s = item_idx % kNS;
-      mbar_wait(&s_empty[s], ((item_idx / kNS) & 1) ^ 1);
+    // the last producer to run dry publishes the sentinel item: it tells the consumers
+    // (and through them the store warp) to stop
+    int fin = 0;
+    if (lane == 0) fin = atomicAdd(&s_fin_count, 1);
+    fin = __shfl_sync(0xffffffffu, fin, 0);
+    if (fin == kProducers - 1) {
+      open_item();
       if (lane == 0) {
+        const int q = atomicAdd(&s_job_ticket, 0);   // jobs started by all producers
         WsItem it;
         it.valid = 0;
-        it.buf = k_local % kNB;
+        it.buf = q % kNB;
         it.first = it.last = 0;
         it.E = it.U = it.UL = it.len = it.len16 = it.N = 0;
         it.pad0_ = it.pad1_ = 0;
-        *stage_item(s) = it;
-        s_stop_job = k_local;
-        mbar_arrive(&s_full[s]);
+        *stage_item(st_s) = it;
+        s_stop_job = q;
+        mbar_arrive(&s_full[st_s]);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kStoreWarp) {
     // ================================================================= store warp
     if (lane == 0) {
       for (int k = 0;; ++k) {
@@ -991,16 +1011,18 @@ mask_expand_ws_kernel(const ExpandParams p) {
         fence_proxy_async_smem();
         bulk_s2g(rec.dst, s_out + static_cast<size_t>(b) * chunk, static_cast<uint32_t>(rec.len16));
         bulk_commit();
-        bulk_wait_read<1>();                     // the previous chunk has left shared memory
-        if (k >= 1) mbar_arrive(&s_free[(k - 1) % kNB]);
+        bulk_wait_read<0>();                     // the chunk has left shared memory
+        mbar_arrive(&s_free[b]);
       }
       bulk_wait_all<0>();
     }
   } else {
     // ================================================================= consumers
-    const int cw = warp - 2;
-    const int ctid = tid - 64;
-    int clean0 = 0, clean1 = 0, clean2 = 0;   // zero prefix of each chunk buffer
+    const int cw = warp;     // consumers are warps 0 .. kWsConsumerWarps-1
+    const int ctid = tid;
+    int clean_of[kNB];   // zero prefix of each chunk buffer (static indexing only -> registers)
+#pragma unroll
+    for (int i = 0; i < kNB; ++i) clean_of[i] = 0;
     for (int item_idx = 0;; ++item_idx) {
       const int s = item_idx % kNS;
       mbar_wait(&s_full[s], (item_idx / kNS) & 1);
@@ -1015,7 +1037,10 @@ mask_expand_ws_kernel(const ExpandParams p) {
       const WsEntry *entries = stage_entries(s);
       const uint32_t *units = stage_units(s);
       if (it.first) {
-        int clean = (it.buf == 0) ? clean0 : ((it.buf == 1) ? clean1 : clean2);
+        int clean = 0;
+#pragma unroll
+        for (int i = 0; i < kNB; ++i)
+          if (it.buf == i) clean = clean_of[i];
         if (clean < it.len16) {
           uint4 *o4 = reinterpret_cast<uint4 *>(out);
           const int n16 = it.len16 >> 4;
@@ -1023,7 +1048,9 @@ mask_expand_ws_kernel(const ExpandParams p) {
             o4[i] = make_uint4(0u, 0u, 0u, 0u);
           clean = it.len16;
         }
-        if (it.buf == 0) clean0 = clean; else if (it.buf == 1) clean1 = clean; else clean2 = clean;
+#pragma unroll
+        for (int i = 0; i < kNB; ++i)
+          if (it.buf == i) clean_of[i] = clean;
       }
       // ---- vertical blend, in place: slot[0] = 0, slot[1+i] = v_i, slot[mw+1] = 0
       for (int ei = cw; ei < it.E; ei += kWsConsumerWarps) {
@@ -1096,7 +1123,9 @@ mask_expand_ws_kernel(const ExpandParams p) {
         }
       }
       if (it.U > 0) {
-        if (it.buf == 0) clean0 = 0; else if (it.buf == 1) clean1 = 0; else clean2 = 0;
+#pragma unroll
+        for (int i = 0; i < kNB; ++i)
+          if (it.buf == i) clean_of[i] = 0;
       }
       fence_proxy_async_smem();   // staging / chunk writes before the TMA touches them again
       __syncwarp();
@@ -1248,18 +1277,31 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   const char *impl = getenv("MRX_EXPAND_IMPL");
   const bool use_v2 = impl != nullptr && strcmp(impl, "v2") == 0;
   if (!use_v2) {
-    // warp-specialised kernel: one persistent CTA per SM
-    const size_t smem = static_cast<size_t>(kNB) * chunk_bytes + kNS * ws_stage_bytes(mw) +
-                        static_cast<size_t>(kBoxCache) * (sizeof(int4) + sizeof(BoxAux) + sizeof(ActBox)) +
-                        static_cast<size_t>(B + 1) * sizeof(int);
-    MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(max_optin),
-                        "mrx_mask_expand: %zu B shared memory > device limit %d (chunk_bytes too "
-                        "large)",
-                        smem, max_optin);
-    MRX_CUDA(cudaFuncSetAttribute(mask_expand_ws_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // warp-specialised kernel: one persistent CTA per SM; as many chunk buffers as fit
+    const size_t fixed = kNS * ws_stage_bytes(mw) +
+                         static_cast<size_t>(kProducers) * kBoxCache * (sizeof(int4) + sizeof(BoxAux) + sizeof(ActBox)) +
+                         static_cast<size_t>(B + 1) * sizeof(int) + 1024;
+    int nb = static_cast<int>((static_cast<size_t>(max_optin) - fixed) / chunk_bytes);
+    if (nb > kMaxNB) nb = kMaxNB;
+    {
+      const char *e = getenv("MRX_EXPAND_NB");
+      if (e && atoi(e) >= 2 && atoi(e) < nb) nb = atoi(e);
+    }
+    MRX_CHECK_SUPPORTED(nb >= 2 && fixed < static_cast<size_t>(max_optin),
+                        "mrx_mask_expand: chunk_bytes %d too large for %d B of shared memory",
+                        chunk_bytes, max_optin);
+    const size_t smem = static_cast<size_t>(nb) * chunk_bytes + fixed - 1024;
+    void (*kern)(const ExpandParams) = nullptr;
+    switch (nb) {
+      case 2: kern = mask_expand_ws_kernel<2>; break;
+      case 3: kern = mask_expand_ws_kernel<3>; break;
+      case 4: kern = mask_expand_ws_kernel<4>; break;
+      case 5: kern = mask_expand_ws_kernel<5>; break;
+      default: kern = mask_expand_ws_kernel<6>; break;
+    }
+    MRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-    mask_expand_ws_kernel<<<sms, kWsThreads, smem, st>>>(prm);
+    kern<<<sms, kWsThreads, smem, st>>>(prm);
     MRX_LAUNCH_CHECK("mask_expand_ws_kernel");
     return MRX_OK;
   }
