@@ -102,6 +102,57 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   } while (!done);
 }
 
+// ---- variants taking 32-bit shared-window addresses (no generic->shared conversion per call)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase
+// completes (or the hint elapses) instead of spinning through the issue slots
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+  } while (!done);
+}
+
+// one try_wait with an explicit suspend-time hint (ns); returns whether the phase completed
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return done != 0;
+}
+
+__device__ __forceinline__ void bulk_g2s_a(uint32_t smem_dst, const void *gmem_src, uint32_t bytes,
+                                           uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_dst),
+      "l"(gmem_src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
 // 1-D TMA: global -> shared, completion reported to an mbarrier (SASS: UBLKCP).
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,

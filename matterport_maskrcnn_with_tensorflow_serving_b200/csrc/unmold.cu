@@ -526,13 +526,13 @@ mask_expand_kernel(const ExpandParams p) {
 //
 //   warps 30,31 producers: fetch work units, lists the (box,row) entries of each chunk,
 //                          issues the 1-D TMA loads of their tile rows, cuts spans into units
-//   warp 29     store    : when a chunk is complete, one bulk (TMA) store shared -> HBM
-//   warps 0..28 consumers: zero fill, vertical blend, span sampling into the shared chunk
+//   warps 28,29 store    : when a chunk is complete, one bulk (TMA) store shared -> HBM
+//   warps 0..27 consumers: zero fill, vertical blend, span sampling into the shared chunk
 //
 // Rings in shared memory, all hand-offs through mbarriers (no __syncthreads in steady state):
 //   item stages  (kNS): staging rows + entries + units + header     full[s] / empty[s]
 //   chunk buffers(kNB): the bytes of one job                        done[b] / free[b]
-// A job is one chunk of a canvas; an item is one pass over <= kEMax entries and <= kUMax
+// A job is one chunk of a canvas; an item is one pass over <= kWsEMax entries and <= kUMax
 // span units of a job (first item zero-fills the chunk, last item releases it to the store
 // warp).
 //
@@ -545,8 +545,10 @@ mask_expand_kernel(const ExpandParams p) {
 constexpr int kWsThreads = 1024;
 constexpr int kWsWarps = kWsThreads / 32;
 constexpr int kProducers = 2;                       // producer warps (highest warp ids)
-constexpr int kWsConsumerWarps = kWsWarps - kProducers - 1;
+constexpr int kStoreWarps = 1;                      // each keeps one bulk store in flight
+constexpr int kWsConsumerWarps = kWsWarps - kProducers - kStoreWarps;
 constexpr int kWsConsumerThreads = kWsConsumerWarps * 32;
+constexpr int kWsEMax = 64;   // entries per item (ws kernel)
 constexpr int kMaxNB = 6;   // chunk buffers: template parameter kNB in [2, kMaxNB]
 constexpr int kNS = 3;
 constexpr int kUMax = 512;
@@ -556,7 +558,7 @@ constexpr int kBandRows = 32;
 constexpr int kFlatGroup = 8;
 constexpr int kMinUnitShift = 2;   // span units are at least 128 columns (4 sampling steps)
 constexpr int kFirstProducerWarp = kWsWarps - kProducers;   // highest warp ids: favoured by the issue arbiter
-constexpr int kStoreWarp = kFirstProducerWarp - 1;
+constexpr int kFirstStoreWarp = kFirstProducerWarp - kStoreWarps;
 static_assert(kNS >= kProducers + 1, "need a free stage beyond the ones being built");
 
 struct __align__(16) WsEntry {
@@ -606,7 +608,7 @@ __device__ __forceinline__ BoxAux make_aux(const int4 bx, int mw) {
 }
 
 __host__ __device__ constexpr size_t ws_stage_bytes(int mw) {
-  return static_cast<size_t>(kEMax) * 2 * mw * sizeof(float) + kEMax * sizeof(WsEntry) +
+  return static_cast<size_t>(kWsEMax) * 2 * mw * sizeof(float) + kWsEMax * sizeof(WsEntry) +
          kUMax * sizeof(uint32_t) + sizeof(WsItem);
 }
 
@@ -641,17 +643,17 @@ mask_expand_ws_kernel(const ExpandParams p) {
   auto stage_rows = [&](int s) { return reinterpret_cast<float *>(stage_base + s * stage_bytes); };
   auto stage_entries = [&](int s) {
     return reinterpret_cast<WsEntry *>(stage_base + s * stage_bytes +
-                                       static_cast<size_t>(kEMax) * slot_bytes);
+                                       static_cast<size_t>(kWsEMax) * slot_bytes);
   };
   auto stage_units = [&](int s) {
     return reinterpret_cast<uint32_t *>(stage_base + s * stage_bytes +
-                                        static_cast<size_t>(kEMax) * slot_bytes +
-                                        kEMax * sizeof(WsEntry));
+                                        static_cast<size_t>(kWsEMax) * slot_bytes +
+                                        kWsEMax * sizeof(WsEntry));
   };
   auto stage_item = [&](int s) {
     return reinterpret_cast<WsItem *>(stage_base + s * stage_bytes +
-                                      static_cast<size_t>(kEMax) * slot_bytes +
-                                      kEMax * sizeof(WsEntry) + kUMax * sizeof(uint32_t));
+                                      static_cast<size_t>(kWsEMax) * slot_bytes +
+                                      kWsEMax * sizeof(WsEntry) + kUMax * sizeof(uint32_t));
   };
   unsigned char *after = stage_base + kNS * stage_bytes;
   constexpr size_t kTableBytes = kBoxCache * (sizeof(int4) + sizeof(BoxAux) + sizeof(ActBox));
@@ -690,7 +692,7 @@ mask_expand_ws_kernel(const ExpandParams p) {
       s_total = carry;
     }
   }
-  if (warp == kStoreWarp && lane == 0) {
+  if (warp == kFirstStoreWarp && lane == 0) {
     for (int s = 0; s < kNS; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], kWsConsumerWarps);
@@ -707,6 +709,8 @@ mask_expand_ws_kernel(const ExpandParams p) {
   }
   __syncthreads();
   const int total_units = s_total;
+  const uint32_t a_full = smem_u32(&s_full[0]), a_empty = smem_u32(&s_empty[0]);
+  const uint32_t a_done = smem_u32(&s_done[0]), a_free = smem_u32(&s_free[0]);
 
   if (warp >= kFirstProducerWarp) {
     // ================================================================= producers
@@ -723,7 +727,7 @@ mask_expand_ws_kernel(const ExpandParams p) {
       if (lane == 0) item_idx = atomicAdd(&s_item_ticket, 1);
       item_idx = __shfl_sync(0xffffffffu, item_idx, 0);
       st_s = item_idx % kNS;
-      mbar_wait(&s_empty[st_s], ((item_idx / kNS) & 1) ^ 1);   // consumers are done with the stage
+      mbar_wait_a(a_empty + 8 * st_s, ((item_idx / kNS) & 1) ^ 1);   // consumers are done with the stage
       st_rows = stage_rows(st_s);
       st_entries = stage_entries(st_s);
       st_units = stage_units(st_s);
@@ -748,14 +752,14 @@ mask_expand_ws_kernel(const ExpandParams p) {
         *stage_item(st_s) = it;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_full[st_s]);
+      if (lane == 0) mbar_arrive_a(a_full + 8 * st_s);
     };
     auto begin_job = [&](unsigned char *dst, int len16) -> int {
       int q = 0;
       if (lane == 0) q = atomicAdd(&s_job_ticket, 1);
       q = __shfl_sync(0xffffffffu, q, 0);
       const int buf = q % kNB;
-      mbar_wait(&s_free[buf], ((q / kNB) & 1) ^ 1);            // chunk buffer drained
+      mbar_wait_a(a_free + 8 * buf, ((q / kNB) & 1) ^ 1);      // chunk buffer drained
       if (lane == 0) {
         s_store[buf].dst = dst;
         s_store[buf].len16 = len16;
@@ -776,9 +780,9 @@ mask_expand_ws_kernel(const ExpandParams p) {
         if (lane >= o) incl += u;
       }
       const int utotal = __shfl_sync(0xffffffffu, incl, 31);
-      if (st_E + ecount > kEMax || st_U + utotal > kUMax) return false;
+      if (st_E + ecount > kWsEMax || st_U + utotal > kUMax) return false;
       if (ecount > 0) {
-        if (lane == 0) mbar_expect_tx(&s_full[st_s], ecount * slot_bytes);
+        if (lane == 0) mbar_expect_tx_a(a_full + 8 * st_s, ecount * slot_bytes);
         __syncwarp();
         if (valid) {
           const int slot = st_E + __popc(bal & ((1u << lane) - 1u));
@@ -810,8 +814,8 @@ mask_expand_ws_kernel(const ExpandParams p) {
           e.pad0_ = 0;
           e.pad1_ = 0;
           st_entries[slot] = e;
-          bulk_g2s(st_rows + slot * slot_floats,
-                   tiles_b + (static_cast<size_t>(n) * mh + jc) * mw, slot_bytes, &s_full[st_s]);
+          bulk_g2s_a(smem_u32(st_rows) + slot * slot_bytes,
+                     tiles_b + (n * mh + jc) * mw, slot_bytes, a_full + 8 * st_s);
           uint32_t *up = st_units + st_U + (incl - nu);
           for (int j = 0; j < nu; ++j)
             up[j] = (static_cast<uint32_t>(slot) << 24) |
@@ -824,7 +828,7 @@ mask_expand_ws_kernel(const ExpandParams p) {
     };
     // smallest shift such that a span of `span_max` columns has <= kMaxUnitsPerEntry units
     auto unit_shift = [&](int span_max) -> int {
-      int sh = kMinUnitShift;
+      int sh = ((p.flags >> 4) & 7) ? ((p.flags >> 4) & 7) : kMinUnitShift;
       while ((32 << sh) * kMaxUnitsPerEntry < span_max) ++sh;
       return sh;
     };
@@ -993,26 +997,42 @@ mask_expand_ws_kernel(const ExpandParams p) {
         it.valid = 0;
         it.buf = q % kNB;
         it.first = it.last = 0;
-        it.E = it.U = it.UL = it.len = it.len16 = it.N = 0;
+        it.E = q;            // sentinel: first job ticket that does not exist
+        it.U = it.UL = it.len = it.len16 = it.N = 0;
         it.pad0_ = it.pad1_ = 0;
         *stage_item(st_s) = it;
         s_stop_job = q;
-        mbar_arrive(&s_full[st_s]);
+        mbar_arrive_a(a_full + 8 * st_s);
       }
     }
-  } else if (warp == kStoreWarp) {
-    // ================================================================= store warp
+  } else if (warp >= kFirstStoreWarp) {
+    // ================================================================= store warps
+    // store warp j owns the chunk buffers b with b % kStoreWarps == j (so every done[]
+    // barrier has a single waiter that sees each of its phases) and waits for its own chunk
+    // to leave shared memory before recycling the buffer: kStoreWarps bulk stores in flight
     if (lane == 0) {
+      const int me = warp - kFirstStoreWarp;
       for (int k = 0;; ++k) {
         const int b = k % kNB;
-        mbar_wait(&s_done[b], (k / kNB) & 1);
-        if (s_stop_job == k) break;
+        if ((b % kStoreWarps) != me) continue;
+        // wait for job k, or learn that it does not exist (the last producer publishes the
+        // number of jobs in s_stop_job; real jobs always complete their done[] phase)
+        bool have = false;
+        while (true) {
+          have = mbar_try_wait_a(a_done + 8 * b, (k / kNB) & 1, 1000u);
+          if (have) break;
+          const int stop = s_stop_job;
+          if (stop >= 0 && k >= stop) break;
+        }
+        if (!have) break;
         const StoreRec rec = s_store[b];
         fence_proxy_async_smem();
-        bulk_s2g(rec.dst, s_out + static_cast<size_t>(b) * chunk, static_cast<uint32_t>(rec.len16));
-        bulk_commit();
-        bulk_wait_read<0>();                     // the chunk has left shared memory
-        mbar_arrive(&s_free[b]);
+        if (!(p.flags & 0x400)) {
+          bulk_s2g(rec.dst, s_out + static_cast<size_t>(b) * chunk, static_cast<uint32_t>(rec.len16));
+          bulk_commit();
+          bulk_wait_read<0>();                   // the chunk has left shared memory
+        }
+        mbar_arrive_a(a_free + 8 * b);
       }
       bulk_wait_all<0>();
     }
@@ -1023,12 +1043,14 @@ mask_expand_ws_kernel(const ExpandParams p) {
     int clean_of[kNB];   // zero prefix of each chunk buffer (static indexing only -> registers)
 #pragma unroll
     for (int i = 0; i < kNB; ++i) clean_of[i] = 0;
-    for (int item_idx = 0;; ++item_idx) {
-      const int s = item_idx % kNS;
-      mbar_wait(&s_full[s], (item_idx / kNS) & 1);
+    int s = -1;
+    uint32_t full_parity = 1;
+    while (true) {
+      if (++s == kNS) s = 0;
+      if (s == 0) full_parity ^= 1;
+      mbar_wait_a(a_full + 8 * s, full_parity);
       const WsItem it = *stage_item(s);
       if (!it.valid) {
-        if (lane == 0) mbar_arrive(&s_done[it.buf]);
         break;
       }
       unsigned char *out = s_out + static_cast<size_t>(it.buf) * chunk;
@@ -1041,7 +1063,7 @@ mask_expand_ws_kernel(const ExpandParams p) {
 #pragma unroll
         for (int i = 0; i < kNB; ++i)
           if (it.buf == i) clean = clean_of[i];
-        if (clean < it.len16) {
+        if (clean < it.len16 && !(p.flags & 0x200)) {
           uint4 *o4 = reinterpret_cast<uint4 *>(out);
           const int n16 = it.len16 >> 4;
           for (int i = (clean >> 4) + ctid; i < n16; i += kWsConsumerThreads)
@@ -1079,7 +1101,7 @@ mask_expand_ws_kernel(const ExpandParams p) {
       // ---- span units
       const unsigned ulen = static_cast<unsigned>(it.len);
       const unsigned ostep = 32u * it.N;
-      for (int u = cw; u < it.U; u += kWsConsumerWarps) {
+      for (int u = cw; u < ((p.flags & 0x100) ? 0 : it.U); u += kWsConsumerWarps) {
         const uint32_t unit = units[u];
         const int ei = static_cast<int>(unit >> 24);
         const int x0 = static_cast<int>(unit & 0xffffffu);
@@ -1130,8 +1152,8 @@ mask_expand_ws_kernel(const ExpandParams p) {
       fence_proxy_async_smem();   // staging / chunk writes before the TMA touches them again
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&s_empty[s]);
-        if (it.last) mbar_arrive(&s_done[it.buf]);
+        mbar_arrive_a(a_empty + 8 * s);
+        if (it.last) mbar_arrive_a(a_done + 8 * it.buf);
       }
     }
   }
