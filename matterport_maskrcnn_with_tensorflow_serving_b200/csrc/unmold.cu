@@ -524,10 +524,14 @@ mask_expand_kernel(const ExpandParams p) {
 // mask expand, warp-specialised: ONE persistent CTA per SM, 32 warps
 // =====================================================================================
 //
-//   warps 30,31 producers: fetch work units, lists the (box,row) entries of each chunk,
-//                          issues the 1-D TMA loads of their tile rows, cuts spans into units
-//   warps 28,29 store    : when a chunk is complete, one bulk (TMA) store shared -> HBM
-//   warps 0..27 consumers: zero fill, vertical blend, span sampling into the shared chunk
+//   warps 30,31 producers: fetch work units, list the (box,row) entries of each chunk, issue
+//                          the 1-D TMA loads of their tile rows, cut spans into units
+//   warps 27-29 store    : when a chunk is complete, one bulk (TMA) store shared -> HBM,
+//                          then re-zeroes the buffer (this is the canvas zero fill)
+//   warps 0..26 consumers: kGroups groups of kGroupWarps; a group takes every kGroups-th
+//                          item; a warp takes span units: vertical blend of the two staged
+//                          tile rows into registers (one column per lane), horizontal lerp
+//                          by warp shuffle, >= 0.5, byte store into the shared chunk
 //
 // Rings in shared memory, all hand-offs through mbarriers (no __syncthreads in steady state):
 //   item stages  (kNS): staging rows + entries + units + header     full[s] / empty[s]
@@ -542,16 +546,17 @@ mask_expand_kernel(const ExpandParams p) {
 //     list, spans clipped once); per row only the vertical coordinate changes.
 //   flat mode (any shape): a unit is kFlatGroup consecutive flat chunks; every chunk tests
 //     all (row, box) pairs.  Chunks may start mid-pixel and span rows.
-constexpr int kWsThreads = 1024;
-constexpr int kWsWarps = kWsThreads / 32;
+constexpr int kWsWarps = 32;   // 27 consumers + 3 store + 2 producers
+constexpr int kWsThreads = kWsWarps * 32;
+constexpr int kGroups = 3;                          // consumer groups
+constexpr int kGroupWarps = 9;                      // warps per consumer group
+constexpr int kWsConsumerWarps = kGroups * kGroupWarps;
+constexpr int kStoreWarps = 3;                      // each owns the chunk buffers b % kStoreWarps
 constexpr int kProducers = 2;                       // producer warps (highest warp ids)
-constexpr int kStoreWarps = 1;                      // each keeps one bulk store in flight
-constexpr int kWsConsumerWarps = kWsWarps - kProducers - kStoreWarps;
-constexpr int kWsConsumerThreads = kWsConsumerWarps * 32;
-constexpr int kWsEMax = 64;   // entries per item (ws kernel)
+constexpr int kWsEMax = 32;   // entries per item (ws kernel)
 constexpr int kMaxNB = 6;   // chunk buffers: template parameter kNB in [2, kMaxNB]
-constexpr int kNS = 3;
-constexpr int kUMax = 512;
+constexpr int kNS = 6;   // item stages: two per consumer group
+constexpr int kUMax = 256;
 constexpr int kMaxUnitsPerEntry = kUMax / 32;
 constexpr int kBoxCache = 128;   // per-producer box / aux / active tables
 constexpr int kBandRows = 32;
@@ -559,7 +564,8 @@ constexpr int kFlatGroup = 8;
 constexpr int kMinUnitShift = 2;   // span units are at least 128 columns (4 sampling steps)
 constexpr int kFirstProducerWarp = kWsWarps - kProducers;   // highest warp ids: favoured by the issue arbiter
 constexpr int kFirstStoreWarp = kFirstProducerWarp - kStoreWarps;
-static_assert(kNS >= kProducers + 1, "need a free stage beyond the ones being built");
+static_assert(kNS % kGroups == 0 && kNS >= kProducers + 1, "stage ring must interleave the groups");
+static_assert(kWsConsumerWarps + kStoreWarps + kProducers == kWsWarps, "warp roles");
 
 struct __align__(16) WsEntry {
   int obase;    // byte offset of (row, x=0, n) relative to the chunk start
@@ -605,6 +611,32 @@ __device__ __forceinline__ BoxAux make_aux(const int4 bx, int mw) {
   a.stepQ = (64 * mw) / a.D;
   a.stepR = (64 * mw) - a.stepQ * a.D;
   return a;
+}
+
+// ---- debug watchdog (MRX_DEBUG=1): a wait that gives up after ~2^22 polls and records who
+// was waiting for what, so that a protocol bug shows up as a report instead of a hang
+__device__ int g_ws_debug[64];
+
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int code, int a0,
+                                             int a1, bool enabled) {
+  if (!enabled) {
+    mbar_wait_a(bar, parity);
+    return;
+  }
+  for (int it = 0; it < (1 << 16); ++it) {
+    if (mbar_try_wait_a(bar, parity, 1000u)) return;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    const int slot = atomicAdd(&g_ws_debug[0], 1);
+    if (slot < 12) {
+      int *d = &g_ws_debug[4 + slot * 5];
+      d[0] = code;
+      d[1] = static_cast<int>(blockIdx.x);
+      d[2] = static_cast<int>(threadIdx.x >> 5);
+      d[3] = a0;
+      d[4] = a1;
+    }
+  }
 }
 
 __host__ __device__ constexpr size_t ws_stage_bytes(int mw) {
@@ -668,6 +700,12 @@ mask_expand_ws_kernel(const ExpandParams p) {
   __shared__ int s_total;
   __shared__ volatile int s_stop_job;
   __shared__ int s_item_ticket, s_job_ticket, s_fin_count;
+  // admission control for the parity waits: with several producers, the holders of tickets t
+  // and t + ring_size could otherwise wait on the same barrier for different phases, and a
+  // parity wait is only unambiguous for the oldest of them
+  __shared__ volatile int s_stage_gen[kNS];    // items that passed the empty[] wait, per stage
+  __shared__ volatile int s_buf_gen[kMaxNB];   // jobs that passed the free[] wait, per chunk buffer
+  __shared__ int s_pending[kMaxNB];   // per chunk buffer: outstanding consumer-warp arrivals + producer token
 
   // ---- work-unit table (first producer warp) and barrier init (store warp)
   if (warp == kFirstProducerWarp) {
@@ -695,11 +733,14 @@ mask_expand_ws_kernel(const ExpandParams p) {
   if (warp == kFirstStoreWarp && lane == 0) {
     for (int s = 0; s < kNS; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], kWsConsumerWarps);
+      mbar_init(&s_empty[s], kGroupWarps);
+      s_stage_gen[s] = 0;
     }
     for (int b = 0; b < kNB; ++b) {
-      mbar_init(&s_done[b], kWsConsumerWarps);
+      mbar_init(&s_done[b], 1);
       mbar_init(&s_free[b], 1);
+      s_pending[b] = 0;
+      s_buf_gen[b] = 0;
     }
     s_stop_job = -1;
     s_item_ticket = 0;
@@ -707,10 +748,18 @@ mask_expand_ws_kernel(const ExpandParams p) {
     s_fin_count = 0;
     fence_mbar_init();
   }
+  {
+    // canvas zero fill, part 1: every chunk buffer starts all-zero (the store warp re-zeroes
+    // a buffer after each bulk store)
+    uint4 *o4 = reinterpret_cast<uint4 *>(s_out);
+    const int n16 = (kNB * chunk) >> 4;
+    for (int i = tid; i < n16; i += kWsThreads) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
   const int total_units = s_total;
   const uint32_t a_full = smem_u32(&s_full[0]), a_empty = smem_u32(&s_empty[0]);
   const uint32_t a_done = smem_u32(&s_done[0]), a_free = smem_u32(&s_free[0]);
+  const bool wd = (p.flags & 0x8000) != 0;   // debug watchdog
 
   if (warp >= kFirstProducerWarp) {
     // ================================================================= producers
@@ -727,7 +776,11 @@ mask_expand_ws_kernel(const ExpandParams p) {
       if (lane == 0) item_idx = atomicAdd(&s_item_ticket, 1);
       item_idx = __shfl_sync(0xffffffffu, item_idx, 0);
       st_s = item_idx % kNS;
-      mbar_wait_a(a_empty + 8 * st_s, ((item_idx / kNS) & 1) ^ 1);   // consumers are done with the stage
+      const int gen = item_idx / kNS;
+      while (s_stage_gen[st_s] != gen) __nanosleep(32);      // previous user of the stage is past its wait
+      mbar_wait_wd(a_empty + 8 * st_s, (gen & 1) ^ 1, 1, item_idx, st_s, wd);   // consumers are done with the stage
+      __syncwarp();
+      if (lane == 0) s_stage_gen[st_s] = gen + 1;
       st_rows = stage_rows(st_s);
       st_entries = stage_entries(st_s);
       st_units = stage_units(st_s);
@@ -750,6 +803,11 @@ mask_expand_ws_kernel(const ExpandParams p) {
         it.pad0_ = 0;
         it.pad1_ = 0;
         *stage_item(st_s) = it;
+        // kGroupWarps consumer warps will report on this item; the producer's own token
+        // (taken in begin_job) is returned after the job's last item
+        const int add = kGroupWarps - (last ? 1 : 0);
+        const int old = atomicAdd(&s_pending[buf], add);
+        (void)old;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive_a(a_full + 8 * st_s);
@@ -759,10 +817,15 @@ mask_expand_ws_kernel(const ExpandParams p) {
       if (lane == 0) q = atomicAdd(&s_job_ticket, 1);
       q = __shfl_sync(0xffffffffu, q, 0);
       const int buf = q % kNB;
-      mbar_wait_a(a_free + 8 * buf, ((q / kNB) & 1) ^ 1);      // chunk buffer drained
+      const int bgen = q / kNB;
+      while (s_buf_gen[buf] != bgen) __nanosleep(32);        // previous job on the buffer is past its wait
+      mbar_wait_wd(a_free + 8 * buf, (bgen & 1) ^ 1, 2, q, buf, wd);      // chunk buffer drained
+      __syncwarp();
+      if (lane == 0) s_buf_gen[buf] = bgen + 1;
       if (lane == 0) {
         s_store[buf].dst = dst;
         s_store[buf].len16 = len16;
+        s_pending[buf] = 1;   // producer token: the job cannot complete before its last item is out
       }
       return buf;
     };
@@ -990,170 +1053,163 @@ mask_expand_ws_kernel(const ExpandParams p) {
     if (lane == 0) fin = atomicAdd(&s_fin_count, 1);
     fin = __shfl_sync(0xffffffffu, fin, 0);
     if (fin == kProducers - 1) {
-      open_item();
-      if (lane == 0) {
-        const int q = atomicAdd(&s_job_ticket, 0);   // jobs started by all producers
-        WsItem it;
-        it.valid = 0;
-        it.buf = q % kNB;
-        it.first = it.last = 0;
-        it.E = q;            // sentinel: first job ticket that does not exist
-        it.U = it.UL = it.len = it.len16 = it.N = 0;
-        it.pad0_ = it.pad1_ = 0;
-        *stage_item(st_s) = it;
-        s_stop_job = q;
-        mbar_arrive_a(a_full + 8 * st_s);
+      int q = 0;
+      if (lane == 0) q = atomicAdd(&s_job_ticket, 0);   // jobs started by all producers
+      q = __shfl_sync(0xffffffffu, q, 0);
+      for (int g = 0; g < kGroups; ++g) {   // consecutive tickets reach every group once
+        open_item();
+        if (lane == 0) {
+          WsItem it;
+          it.valid = 0;
+          it.buf = 0;
+          it.first = it.last = 0;
+          it.E = it.U = it.UL = it.len = it.len16 = it.N = 0;
+          it.pad0_ = it.pad1_ = 0;
+          *stage_item(st_s) = it;
+          s_stop_job = q;
+          mbar_arrive_a(a_full + 8 * st_s);
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= kFirstStoreWarp) {
     // ================================================================= store warps
-    // store warp j owns the chunk buffers b with b % kStoreWarps == j (so every done[]
-    // barrier has a single waiter that sees each of its phases) and waits for its own chunk
-    // to leave shared memory before recycling the buffer: kStoreWarps bulk stores in flight
-    if (lane == 0) {
-      const int me = warp - kFirstStoreWarp;
-      for (int k = 0;; ++k) {
-        const int b = k % kNB;
-        if ((b % kStoreWarps) != me) continue;
-        // wait for job k, or learn that it does not exist (the last producer publishes the
-        // number of jobs in s_stop_job; real jobs always complete their done[] phase)
-        bool have = false;
-        while (true) {
-          have = mbar_try_wait_a(a_done + 8 * b, (k / kNB) & 1, 1000u);
-          if (have) break;
-          const int stop = s_stop_job;
-          if (stop >= 0 && k >= stop) break;
+    // store warp j owns the chunk buffers b with b % kStoreWarps == j (every done[] barrier has
+    // a single waiter that sees each of its phases): store, drain and re-zero run in parallel
+    // on different buffers
+    const int me = warp - kFirstStoreWarp;
+    const int n_store = ((p.flags >> 12) & 3) ? ((p.flags >> 12) & 3) : kStoreWarps;
+    for (int k = 0; me < n_store; ++k) {
+      const int b = k % kNB;
+      if ((b % n_store) != me) continue;
+      // wait for job k, or learn that it does not exist (the last producer publishes the
+      // number of jobs in s_stop_job; real jobs always complete their done[] phase)
+      bool have = false;
+      for (int it = 0;; ++it) {
+        have = mbar_try_wait_a(a_done + 8 * b, (k / kNB) & 1, 1000u);
+        if (have) break;
+        const int stop = s_stop_job;
+        if (stop >= 0 && k >= stop) break;
+        if (wd && it > (1 << 16)) {
+          if (lane == 0) {
+            const int slot = atomicAdd(&g_ws_debug[0], 1);
+            if (slot < 12) {
+              int *d = &g_ws_debug[4 + slot * 5];
+              d[0] = 4; d[1] = static_cast<int>(blockIdx.x); d[2] = warp; d[3] = k; d[4] = s_pending[b] * 1000 + stop;
+            }
+          }
+          break;
         }
-        if (!have) break;
-        const StoreRec rec = s_store[b];
+      }
+      if (!have) break;
+      const StoreRec rec = s_store[b];
+      unsigned char *buf = s_out + static_cast<size_t>(b) * chunk;
+      if (lane == 0) {
         fence_proxy_async_smem();
         if (!(p.flags & 0x400)) {
-          bulk_s2g(rec.dst, s_out + static_cast<size_t>(b) * chunk, static_cast<uint32_t>(rec.len16));
+          bulk_s2g(rec.dst, buf, static_cast<uint32_t>(rec.len16));
           bulk_commit();
           bulk_wait_read<0>();                   // the chunk has left shared memory
         }
-        mbar_arrive_a(a_free + 8 * b);
       }
-      bulk_wait_all<0>();
+      __syncwarp();
+      // canvas zero fill, part 2: the buffer goes back to the pool all-zero
+      if (!(p.flags & 0x200)) {
+        uint4 *o4 = reinterpret_cast<uint4 *>(buf);
+        const int n16 = rec.len16 >> 4;
+        int i = lane;
+        for (; i + 96 < n16; i += 128) {
+          o4[i] = make_uint4(0u, 0u, 0u, 0u);
+          o4[i + 32] = make_uint4(0u, 0u, 0u, 0u);
+          o4[i + 64] = make_uint4(0u, 0u, 0u, 0u);
+          o4[i + 96] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (; i < n16; i += 32) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(a_free + 8 * b);
     }
+    if (lane == 0) bulk_wait_all<0>();
   } else {
     // ================================================================= consumers
-    const int cw = warp;     // consumers are warps 0 .. kWsConsumerWarps-1
-    const int ctid = tid;
-    int clean_of[kNB];   // zero prefix of each chunk buffer (static indexing only -> registers)
-#pragma unroll
-    for (int i = 0; i < kNB; ++i) clean_of[i] = 0;
-    int s = -1;
-    uint32_t full_parity = 1;
+    const int grp = warp / kGroupWarps;      // consumers are warps 0 .. kWsConsumerWarps-1
+    const int gw = warp - grp * kGroupWarps;
+    int s = grp - kGroups;                   // this group's items: tickets grp, grp + kGroups, ...
+    uint32_t full_parity = 0;
     while (true) {
-      if (++s == kNS) s = 0;
-      if (s == 0) full_parity ^= 1;
-      mbar_wait_a(a_full + 8 * s, full_parity);
-      const WsItem it = *stage_item(s);
-      if (!it.valid) {
-        break;
+      s += kGroups;
+      if (s >= kNS) {
+        s -= kNS;
+        full_parity ^= 1;
       }
-      unsigned char *out = s_out + static_cast<size_t>(it.buf) * chunk;
-      const uint32_t out_addr = smem_u32(out);
-      float *rows = stage_rows(s);
+      mbar_wait_wd(a_full + 8 * s, full_parity, 3, s, static_cast<int>(full_parity), wd);
+      const WsItem it = *stage_item(s);
+      if (!it.valid) break;
+      const uint32_t out_addr = smem_u32(s_out + static_cast<size_t>(it.buf) * chunk);
+      const float *rows = stage_rows(s);
       const WsEntry *entries = stage_entries(s);
       const uint32_t *units = stage_units(s);
-      if (it.first) {
-        int clean = 0;
-#pragma unroll
-        for (int i = 0; i < kNB; ++i)
-          if (it.buf == i) clean = clean_of[i];
-        if (clean < it.len16 && !(p.flags & 0x200)) {
-          uint4 *o4 = reinterpret_cast<uint4 *>(out);
-          const int n16 = it.len16 >> 4;
-          for (int i = (clean >> 4) + ctid; i < n16; i += kWsConsumerThreads)
-            o4[i] = make_uint4(0u, 0u, 0u, 0u);
-          clean = it.len16;
-        }
-#pragma unroll
-        for (int i = 0; i < kNB; ++i)
-          if (it.buf == i) clean_of[i] = clean;
-      }
-      // ---- vertical blend, in place: slot[0] = 0, slot[1+i] = v_i, slot[mw+1] = 0
-      for (int ei = cw; ei < it.E; ei += kWsConsumerWarps) {
-        const WsEntry e = entries[ei];
-        float *slot = rows + ei * slot_floats;
-        float v0 = 0.f, v1 = 0.f;
-        if (lane < mw) {
-          const float top = (e.otop >= 0) ? slot[e.otop + lane] : 0.f;
-          const float bot = (e.obot >= 0) ? slot[e.obot + lane] : 0.f;
-          v0 = fmaf(e.wy, bot - top, top);
-        }
-        if (lane + 32 < mw) {
-          const float top = (e.otop >= 0) ? slot[e.otop + lane + 32] : 0.f;
-          const float bot = (e.obot >= 0) ? slot[e.obot + lane + 32] : 0.f;
-          v1 = fmaf(e.wy, bot - top, top);
-        }
-        __syncwarp();
-        if (lane < mw) slot[1 + lane] = v0;
-        if (lane + 32 < mw) slot[1 + lane + 32] = v1;
-        if (lane == 0) {
-          slot[0] = 0.f;
-          slot[mw + 1] = 0.f;
-        }
-      }
-      named_bar_sync(1, kWsConsumerThreads);   // zero fill + blended rows visible to all consumers
-      // ---- span units
       const unsigned ulen = static_cast<unsigned>(it.len);
       const unsigned ostep = 32u * it.N;
-      for (int u = cw; u < ((p.flags & 0x100) ? 0 : it.U); u += kWsConsumerWarps) {
+      const int n_units = (p.flags & 0x100) ? 0 : it.U;
+      for (int u = gw; u < n_units; u += kGroupWarps) {
         const uint32_t unit = units[u];
         const int ei = static_cast<int>(unit >> 24);
         const int x0 = static_cast<int>(unit & 0xffffffu);
         const WsEntry e = entries[ei];
         const float *slot = rows + ei * slot_floats;
+        // vertical blend of the two staged tile rows, one column per lane:
+        // lane l holds B[l] with B[0] = 0, B[1+i] = blend(i), B[mw+1] = 0   (mw <= 30)
+        float bl = 0.f;
+        {
+          const int i = lane - 1;
+          if (i >= 0 && i < mw) {
+            const float top = (e.otop >= 0) ? slot[e.otop + i] : 0.f;
+            const float bot = (e.obot >= 0) ? slot[e.obot + i] : 0.f;
+            bl = fmaf(e.wy, bot - top, top);
+          }
+        }
         const int xend = min(x0 + it.UL, e.xb);
         int x = x0 + lane;
-        if (x < xend) {
-          int i0, rem;
-          {
-            const int A = mw * (2 * (x - e.x1) + 1) - (e.D >> 1);
-            i0 = __float2int_rd(static_cast<float>(A) * e.invD);
-            rem = A - i0 * e.D;
-            if (rem < 0) {
-              --i0;
-              rem += e.D;
-            } else if (rem >= e.D) {
-              ++i0;
-              rem -= e.D;
-            }
+        // exact source coordinate of this lane's first column, then 32 columns per step
+        int idx, rem;
+        {
+          const int A = mw * (2 * (x - e.x1) + 1) - (e.D >> 1);
+          int i0 = __float2int_rd(static_cast<float>(A) * e.invD);
+          rem = A - i0 * e.D;
+          if (rem < 0) {
+            --i0;
+            rem += e.D;
+          } else if (rem >= e.D) {
+            ++i0;
+            rem -= e.D;
           }
-          const float *rp = slot + 1 + i0;
-          unsigned off = static_cast<unsigned>(e.obase + x * it.N);
-          while (true) {
-            const float wx = static_cast<float>(rem) * e.invD;
-            const float a = rp[0];
-            const float bq = rp[1];
-            const float v = fmaf(wx, bq - a, a);
-            if (v >= 0.5f && off < ulen)
-              asm volatile("st.shared.u8 [%0], %1;" ::"r"(out_addr + off), "r"(1u) : "memory");
-            x += 32;
-            if (x >= xend) break;
-            off += ostep;
-            rem += e.stepR;
-            rp += e.stepQ;
-            if (rem >= e.D) {
-              rem -= e.D;
-              ++rp;
-            }
+          idx = i0 + 1;   // B[idx], B[idx+1] are the two taps
+        }
+        unsigned off = static_cast<unsigned>(e.obase + x * it.N);
+        for (int xs = x0; xs < xend; xs += 32) {   // warp-uniform trip count (shuffles inside)
+          const float wx = static_cast<float>(rem) * e.invD;
+          const float a = __shfl_sync(0xffffffffu, bl, idx);
+          const float bq = __shfl_sync(0xffffffffu, bl, idx + 1);
+          const float v = fmaf(wx, bq - a, a);
+          if (v >= 0.5f && x < xend && off < ulen)
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(out_addr + off), "r"(1u) : "memory");
+          x += 32;
+          off += ostep;
+          rem += e.stepR;
+          idx += e.stepQ;
+          if (rem >= e.D) {
+            rem -= e.D;
+            ++idx;
           }
         }
       }
-      if (it.U > 0) {
-#pragma unroll
-        for (int i = 0; i < kNB; ++i)
-          if (it.buf == i) clean_of[i] = 0;
-      }
-      fence_proxy_async_smem();   // staging / chunk writes before the TMA touches them again
+      fence_proxy_async_smem();   // chunk bytes must be visible to the bulk store
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_a(a_empty + 8 * s);
-        if (it.last) mbar_arrive_a(a_done + 8 * it.buf);
+        // report on the job; whoever returns the last outstanding arrival releases the chunk
+        if (atomicSub(&s_pending[it.buf], 1) == 1) mbar_arrive_a(a_done + 8 * it.buf);
       }
     }
   }
@@ -1297,7 +1353,9 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const char *impl = getenv("MRX_EXPAND_IMPL");
-  const bool use_v2 = impl != nullptr && strcmp(impl, "v2") == 0;
+  // the warp-specialised kernel keeps a blended tile row in one warp's registers
+  // (mw + 2 <= 32 lanes); wider tiles take the generic kernel
+  const bool use_v2 = (impl != nullptr && strcmp(impl, "v2") == 0) || mw > 30;
   if (!use_v2) {
     // warp-specialised kernel: one persistent CTA per SM; as many chunk buffers as fit
     const size_t fixed = kNS * ws_stage_bytes(mw) +
@@ -1323,7 +1381,24 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
     }
     MRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
+    const bool dbg = getenv("MRX_DEBUG") != nullptr;
+    if (dbg) {
+      int zero[64] = {0};
+      MRX_CUDA(cudaMemcpyToSymbol(g_ws_debug, zero, sizeof(zero)));
+      prm.flags |= 0x8000;
+    }
     kern<<<sms, kWsThreads, smem, st>>>(prm);
+    if (dbg) {
+      MRX_CUDA(cudaStreamSynchronize(st));
+      int h[64];
+      MRX_CUDA(cudaMemcpyFromSymbol(h, g_ws_debug, sizeof(h)));
+      if (h[0] > 0) {
+        fprintf(stderr, "[mrx ws watchdog] %d stuck waits (nb=%d):\n", h[0], nb);
+        for (int i = 0; i < h[0] && i < 12; ++i)
+          fprintf(stderr, "  code=%d (1=empty 2=free 3=full 4=done) cta=%d warp=%d a0=%d a1=%d\n",
+                  h[4 + i * 5], h[5 + i * 5], h[6 + i * 5], h[7 + i * 5], h[8 + i * 5]);
+      }
+    }
     MRX_LAUNCH_CHECK("mask_expand_ws_kernel");
     return MRX_OK;
   }
