@@ -172,7 +172,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.idx), "-lms", "100"],
+                 "-i", str(self.idx), "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -210,7 +210,8 @@ class ClockSampler:
             return None
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons),
+                "window": "identical untimed load (--load-ms) + the timed region, 50 ms period"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -299,8 +300,16 @@ def run_ours(args, rank, world, local_rank):
     lib = eng.lib
     P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     st = N.stream_ptr(stream)
-    barrier()
+    # clock sampling needs load for longer than a few ms: run the same steps untimed for
+    # --load-ms first (clocks settle, nvidia-smi gets samples), keep sampling through the
+    # timed region
     sampler.start()
+    t_load = time.perf_counter()
+    while (time.perf_counter() - t_load) * 1e3 < args.load_ms:
+        for _ in range(10):
+            eng.enqueue(d_det, d_msk, stream)
+        torch.cuda.synchronize()
+    barrier()
     ev0.record(stream)
     for s in range(args.steps):
         N.check(lib.mrx_unmold_prologue(P(d_det), N.MRX_F32, BATCH, N_INST, CLASSES, P(eng.d_geom),
@@ -398,7 +407,7 @@ def run_ours(args, rank, world, local_rank):
                        "sharding": f"images over {world} rank(s), no data-path collective",
                        "l2": "per-step working set (813 MB in + 3.36 GB out per GPU) exceeds the "
                              "126 MB L2; no explicit flush",
-                       "chunk_bytes": eng.chunk_bytes or 32768, "seed": SEED},
+                       "chunk_bytes": eng.chunk_bytes or 25600, "seed": SEED},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
@@ -422,7 +431,9 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--load-ms", type=float, default=400.0,
+                    help="untimed identical load before the timed region (clock sampling window)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--chunk-bytes", type=int, default=0)

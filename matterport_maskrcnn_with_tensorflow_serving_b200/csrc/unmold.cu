@@ -1323,7 +1323,7 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   MRX_CHECK_ARG(B >= 0 && B <= MRX_MAX_BATCH && R >= 1, "mrx_mask_expand: bad sizes B=%d R=%d",
                 B, R);
   if (int rc = check_mask_dims(mh, mw)) return rc;
-  if (chunk_bytes == 0) chunk_bytes = 51200;
+  if (chunk_bytes == 0) chunk_bytes = 25600;
   MRX_CHECK_ARG(chunk_bytes >= 1024 && (chunk_bytes % 16) == 0,
                 "mrx_mask_expand: chunk_bytes %d must be a multiple of 16, >= 1024", chunk_bytes);
   if (B == 0) return MRX_OK;

@@ -175,3 +175,31 @@ def test_full_size_properties(cuda_device):
             ref = rz >= 0.5
             d = m[y1:y2, x1:x2, i] != ref
             assert not (d & (np.abs(rz - 0.5) > MASK_VALUE_ATOL)).any()
+
+
+@pytest.mark.parametrize("name", ["unmold_small", "unmold_coco_shape"])
+def test_golden_fixture(cuda_device, name):
+    """Committed fixture (tests/golden/make_golden.py): exact ints, masks equal outside the
+    recorded +-1e-6 band around the threshold."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    b, c, s, m = api_utils.unmold_detections(
+        g["detections"].astype(np.float64), g["mrcnn_mask"].astype(np.float64),
+        tuple(g["original_image_shape"]), tuple(g["image_shape"]), tuple(g["window"]))
+    np.testing.assert_array_equal(b, g["boxes"])
+    np.testing.assert_array_equal(c, g["class_ids"])
+    np.testing.assert_array_equal(s, g["scores"])
+    shape = tuple(g["masks_shape"])
+    want = np.unpackbits(g["masks_packed"])[:int(np.prod(shape))].reshape(shape).astype(bool)
+    band = np.unpackbits(g["band_packed"])[:int(np.prod(shape))].reshape(shape).astype(bool)
+    assert m.shape == shape
+    assert not ((m != want) & ~band).any()
+
+
+def test_generic_kernel_path(cuda_device, monkeypatch):
+    """MRX_EXPAND_IMPL=v2 selects the non-specialised kernel (also used for tiles wider than
+    30 columns); it must satisfy the same contract."""
+    monkeypatch.setenv("MRX_EXPAND_IMPL", "v2")
+    im = synth.make_batch(12, 1, (300, 420), 40, num_classes=6)[0]
+    _check_image(im, np.float64)
