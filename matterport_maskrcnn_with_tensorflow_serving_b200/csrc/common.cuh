@@ -116,6 +116,7 @@ __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
 // completes (or the hint elapses) instead of spinning through the issue slots
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t done;
+#pragma unroll 1
   do {
     asm volatile(
         "{\n\t"

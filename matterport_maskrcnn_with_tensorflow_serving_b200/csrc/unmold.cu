@@ -546,13 +546,13 @@ mask_expand_kernel(const ExpandParams p) {
 //     list, spans clipped once); per row only the vertical coordinate changes.
 //   flat mode (any shape): a unit is kFlatGroup consecutive flat chunks; every chunk tests
 //     all (row, box) pairs.  Chunks may start mid-pixel and span rows.
-constexpr int kWsWarps = 32;   // 27 consumers + 3 store + 2 producers
+constexpr int kWsWarps = 32;   // 27 consumers + 2 store + 3 producers
 constexpr int kWsThreads = kWsWarps * 32;
 constexpr int kGroups = 3;                          // consumer groups
 constexpr int kGroupWarps = 9;                      // warps per consumer group
 constexpr int kWsConsumerWarps = kGroups * kGroupWarps;
-constexpr int kStoreWarps = 3;                      // each owns the chunk buffers b % kStoreWarps
-constexpr int kProducers = 2;                       // producer warps (highest warp ids)
+constexpr int kStoreWarps = 2;                      // each owns the chunk buffers b % kStoreWarps
+constexpr int kProducers = 3;                       // producer warps (highest warp ids)
 constexpr int kWsEMax = 32;   // entries per item (ws kernel)
 constexpr int kMaxNB = 6;   // chunk buffers: template parameter kNB in [2, kMaxNB]
 constexpr int kNS = 6;   // item stages: two per consumer group
@@ -619,10 +619,15 @@ __device__ int g_ws_debug[64];
 
 __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int code, int a0,
                                              int a1, bool enabled) {
+#ifndef MRX_WATCHDOG
+  (void)code; (void)a0; (void)a1; (void)enabled;
+  mbar_wait_a(bar, parity);
+#else
   if (!enabled) {
     mbar_wait_a(bar, parity);
     return;
   }
+#pragma unroll 1
   for (int it = 0; it < (1 << 16); ++it) {
     if (mbar_try_wait_a(bar, parity, 1000u)) return;
   }
@@ -637,6 +642,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity, int 
       d[4] = a1;
     }
   }
+#endif
 }
 
 __host__ __device__ constexpr size_t ws_stage_bytes(int mw) {
@@ -1085,11 +1091,13 @@ mask_expand_ws_kernel(const ExpandParams p) {
       // wait for job k, or learn that it does not exist (the last producer publishes the
       // number of jobs in s_stop_job; real jobs always complete their done[] phase)
       bool have = false;
+#pragma unroll 1
       for (int it = 0;; ++it) {
         have = mbar_try_wait_a(a_done + 8 * b, (k / kNB) & 1, 1000u);
         if (have) break;
         const int stop = s_stop_job;
         if (stop >= 0 && k >= stop) break;
+#ifdef MRX_WATCHDOG
         if (wd && it > (1 << 16)) {
           if (lane == 0) {
             const int slot = atomicAdd(&g_ws_debug[0], 1);
@@ -1100,6 +1108,7 @@ mask_expand_ws_kernel(const ExpandParams p) {
           }
           break;
         }
+#endif
       }
       if (!have) break;
       const StoreRec rec = s_store[b];
@@ -1381,7 +1390,11 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
     }
     MRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
+#ifdef MRX_WATCHDOG
     const bool dbg = getenv("MRX_DEBUG") != nullptr;
+#else
+    const bool dbg = false;   // rebuild with -DMRX_WATCHDOG to get the stuck-wait report
+#endif
     if (dbg) {
       int zero[64] = {0};
       MRX_CUDA(cudaMemcpyToSymbol(g_ws_debug, zero, sizeof(zero)));

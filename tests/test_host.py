@@ -159,3 +159,16 @@ def test_gather_to_root_gloo_world_size_2(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK" in outs[0]
+
+
+def test_dropin_shims_resolve_the_reference_imports():
+    """serve.py:21-23 import lines work against dropin/ (run in a clean interpreter)."""
+    code = ("import sys; sys.path.insert(0, %r);"
+            "from api.helpers import utils as api_utils; import configs as cf;"
+            "from model_configs import mconfig as mcf;"
+            "assert callable(api_utils.get_anchors) and callable(api_utils.unmold_detections);"
+            "assert callable(api_utils.load_img);"
+            "assert cf.OUT_DETECTION_SHAPE == (100, 6) and mcf.IMAGE_MAX_DIM == 1024;"
+            "print('ok')") % os.path.join(ROOT, "dropin")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr
