@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MRX_ABI_VERSION 1
+#define MRX_ABI_VERSION 2
 
 #define MRX_OK              0
 #define MRX_E_INVALID      -1   /* bad argument (null pointer, size out of range) */
@@ -84,13 +84,16 @@ int mrx_anchors(float *d_out, int img_h, int img_w,
  *   d_detections [B,R,6] det_dtype      d_geom [B,8] int32
  *   d_boxes [B,R,4] int32   d_class_ids [B,R] int32   d_scores [B,R] det_dtype
  *   d_src_index [B,R] int32 (kept row -> original row)
+ *   d_box_aux [B,R,4] 4-byte words: per kept box the row-invariant constants of the
+ *     horizontal resize coordinate for mask tiles `mw` wide (2*bw, 1/(2*bw) as float bits,
+ *     (64*mw) div/mod 2*bw); consumed by mrx_mask_expand
  *   d_counts [B] int32 (N per image)    d_status [B] int32 (MRX_ST_* bits)
  * C = number of classes in mrcnn_mask's last axis (for the class-range check).
  * Also resets *d_job_counter (uint32) used by mrx_mask_expand's scheduler. */
 int mrx_unmold_prologue(const void *d_detections, int det_dtype, int B, int R, int C,
-                        const int *d_geom,
+                        int mw, const int *d_geom,
                         int *d_boxes, int *d_class_ids, void *d_scores,
-                        int *d_src_index, int *d_counts, int *d_status,
+                        int *d_src_index, int *d_box_aux, int *d_counts, int *d_status,
                         unsigned int *d_job_counter, void *stream);
 
 /* masks = mrcnn_mask[src_index, :, :, class_id] packed to float32 tiles.
@@ -109,8 +112,8 @@ int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype,
  *   chunk_bytes: bytes of canvas one CTA builds in shared memory and stores
  *   with one bulk copy; multiple of 16; 0 = library default.
  *   ctas_per_sm: 0 = as many as fit.                                              */
-int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_counts,
-                    const int *d_geom, const long long *d_canvas_off,
+int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
+                    const int *d_counts, const int *d_geom, const long long *d_canvas_off,
                     unsigned char *d_canvas, int B, int R, int mh, int mw,
                     int chunk_bytes, int ctas_per_sm,
                     unsigned int *d_job_counter, void *stream);

@@ -21,7 +21,7 @@ MRX_ST_CLASS_RANGE = 1
 MRX_ST_BOX_RANGE = 2
 MRX_GEOM_INTS = 8
 MRX_MAX_BATCH = 4096
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class MrxError(RuntimeError):
@@ -38,10 +38,11 @@ SIGNATURES = {
     "mrx_device_props": (_i, [_i, _ip, _ip, _ip, _ip]),
     "mrx_anchor_count": (_i, [_i, _i, _ip, _i, _i, _i, C.POINTER(C.c_longlong)]),
     "mrx_anchors": (_i, [_vp, _i, _i, _dp, _dp, _ip, _i, _i, _i, _vp]),
-    "mrx_unmold_prologue": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp, _vp]),
+    "mrx_unmold_prologue": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _vp]),
     "mrx_gather_tiles": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
-    "mrx_mask_expand": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mrx_mask_expand": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp,
+                             _vp]),
     "mrx_resize_tile_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "mrx_cv2_resize_u8c3": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "mrx_mold_image": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _dp, _i, _vp, _vp, _vp]),

@@ -84,6 +84,7 @@ class UnmoldEngine:
         self.d_class_ids = torch.empty((B, R), dtype=i32, device=dev)
         self.d_scores = torch.empty((B, R), dtype=_torch_dtype(self.det_dtype), device=dev)
         self.d_src_index = torch.empty((B, R), dtype=i32, device=dev)
+        self.d_box_aux = torch.zeros((B, R, 4), dtype=i32, device=dev)
         self.d_counts = torch.zeros((B,), dtype=i32, device=dev)
         self.d_status = torch.zeros((B,), dtype=i32, device=dev)
         self.d_tiles = torch.empty((B, R, self.mh, self.mw), dtype=torch.float32, device=dev)
@@ -148,10 +149,11 @@ class UnmoldEngine:
         st = N.stream_ptr(stream)
         lib = self.lib
         N.check(lib.mrx_unmold_prologue(
-            _ptr(d_detections), _dtype_code(self.det_dtype), n, self.R, self.C,
+            _ptr(d_detections), _dtype_code(self.det_dtype), n, self.R, self.C, self.mw,
             _ptr(self.d_geom), _ptr(self.d_boxes), _ptr(self.d_class_ids),
-            _ptr(self.d_scores), _ptr(self.d_src_index), _ptr(self.d_counts),
-            _ptr(self.d_status), _ptr(self.d_job_counter), st), "mrx_unmold_prologue")
+            _ptr(self.d_scores), _ptr(self.d_src_index), _ptr(self.d_box_aux),
+            _ptr(self.d_counts), _ptr(self.d_status), _ptr(self.d_job_counter), st),
+            "mrx_unmold_prologue")
         N.check(lib.mrx_gather_tiles(
             _ptr(d_mrcnn_mask), _dtype_code(self.mask_dtype), n, self.R, self.mh, self.mw,
             self.C, _ptr(self.d_class_ids), _ptr(self.d_src_index), _ptr(self.d_counts),
@@ -164,7 +166,8 @@ class UnmoldEngine:
         if reset_counter:
             self.d_job_counter.zero_()
         N.check(self.lib.mrx_mask_expand(
-            _ptr(self.d_tiles), _ptr(self.d_boxes), _ptr(self.d_counts), _ptr(self.d_geom),
+            _ptr(self.d_tiles), _ptr(self.d_boxes), _ptr(self.d_box_aux), _ptr(self.d_counts),
+            _ptr(self.d_geom),
             _ptr(self.d_canvas_off), _ptr(self.d_canvas), n, self.R, self.mh, self.mw,
             self.chunk_bytes, self.ctas_per_sm, _ptr(self.d_job_counter),
             N.stream_ptr(stream)), "mrx_mask_expand")

@@ -40,7 +40,7 @@ def test_host_side_argument_validation():
     assert lib.mrx_anchor_count(1024, 1024, strides, 9, 3, 1, C.byref(out)) == -2     # > MRX_MAX_LEVELS
     assert b"n_levels" in lib.mrx_last_error()
     assert lib.mrx_anchors(None, 1024, 1024, None, None, strides, 5, 3, 1, None) == -1
-    assert lib.mrx_mask_expand(None, None, None, None, None, None, 1, 100, 28, 28, 0, 0,
+    assert lib.mrx_mask_expand(None, None, None, None, None, None, None, 1, 100, 28, 28, 0, 0,
                                None, None) == -1
     assert lib.mrx_resize_tile_f32(C.c_void_p(16), 28, 30, 4, 4, C.c_void_p(16), None) == -2  # mw % 4
 
