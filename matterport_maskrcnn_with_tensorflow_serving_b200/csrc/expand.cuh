@@ -30,6 +30,7 @@ struct ExpandParams {
 
 // Launch the warp-specialised kernel (one persistent CTA per SM).  Returns MRX_OK or an error
 // code with mrx_last_error() set.  Requires mw <= 30.
-int launch_expand_ws(const ExpandParams &prm, int sms, int max_smem_optin, cudaStream_t st);
+int launch_expand_ws(const ExpandParams &prm, int sms, int max_smem_optin, cudaStream_t st);    // gen 5
+int launch_expand_ws4(const ExpandParams &prm, int sms, int max_smem_optin, cudaStream_t st);   // gen 4 (default)
 
 }  // namespace mrx

@@ -40,11 +40,11 @@
 
 namespace mrx {
 
-constexpr int kGroups = 3;
-constexpr int kGroupWarps = 9;
+constexpr int kGroups = 6;
+constexpr int kGroupWarps = 4;
 constexpr int kConsumerWarps = kGroups * kGroupWarps;   // warps 0..26
 constexpr int kStoreWarps = 3;                          // store warp j owns buffers b % 3 == j
-constexpr int kProducers = 2;
+constexpr int kProducers = 3;
 constexpr int kWarps = kConsumerWarps + kStoreWarps + kProducers;
 constexpr int kThreads = kWarps * 32;
 constexpr int kFirstStoreWarp = kConsumerWarps;
@@ -54,7 +54,7 @@ constexpr int kMaxNB = 8;     // chunk buffers: template parameter kNB in [2, kM
 constexpr int kSlots = 4;     // staged tile-row pairs per consumer warp
 constexpr int kBandRows = 32;
 constexpr int kFlatGroup = 8;
-static_assert(kWarps == 32 && kNS % kGroups == 0, "warp roles / stage ring");
+static_assert(kWarps <= 32 && kNS % kGroups == 0, "warp roles / stage ring");
 
 struct __align__(16) JobDesc {
   int valid, buf, len, N;
@@ -327,6 +327,10 @@ mask_expand_ws_kernel(const ExpandParams p) {
     const uint32_t my_bar = smem_u32(&s_wbar[warp]);
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t wpar = 0;
+    int c_img = -1, c_base = -1, c_hi = -1;   // which boxes the registers below hold
+    int4 bx = make_int4(0, 0, 0, 0);
+    BoxAux ax;
+    ax.D = 0; ax.invD = 0.f; ax.stepQ = 0; ax.stepR = 0;
     int s = grp - kGroups;        // this group's tickets: grp, grp + kGroups, ...
     uint32_t fpar = 0;
     while (true) {
@@ -350,16 +354,21 @@ mask_expand_ws_kernel(const ExpandParams p) {
         // this warp's boxes, one per lane
         const int n = base + lane;
         const bool have = n < n_hi;
-        int4 bx = make_int4(0, 0, 0, 0);
-        BoxAux ax;
-        ax.D = 0; ax.invD = 0.f; ax.stepQ = 0; ax.stepR = 0;
-        if (have) {
-          bx = __ldg(boxes_b + n);
-          const int4 raw = __ldg(reinterpret_cast<const int4 *>(aux_b + n));
-          ax.D = raw.x;
-          ax.invD = __int_as_float(raw.y);
-          ax.stepQ = raw.z;
-          ax.stepR = raw.w;
+        if (d.img != c_img || base != c_base || n_hi != c_hi) {
+          // (re)load this warp's boxes; consecutive jobs of an image reuse the registers
+          bx = make_int4(0, 0, 0, 0);
+          ax.D = 0;
+          if (have) {
+            bx = __ldg(boxes_b + n);
+            const int4 raw = __ldg(reinterpret_cast<const int4 *>(aux_b + n));
+            ax.D = raw.x;
+            ax.invD = __int_as_float(raw.y);
+            ax.stepQ = raw.z;
+            ax.stepR = raw.w;
+          }
+          c_img = d.img;
+          c_base = base;
+          c_hi = n_hi;
         }
         for (int row = d.r0; row <= d.r1; ++row) {
           const int xlo = max(0, d.g0 - row * d.W);
@@ -396,12 +405,14 @@ mask_expand_ws_kernel(const ExpandParams p) {
             const int rank = __popc(mask & lt_mask);
             const bool mine = ((mask >> lane) & 1u) && rank < kSlots;
             const int cnt = min(__popc(mask), kSlots);
-            if (lane == 0) mbar_arrive_expect_tx(&s_wbar[warp], cnt * slot_bytes);
-            if (mine)
-              bulk_g2s_a(my_slots_a + rank * slot_bytes, tiles_b + (n * mh + jc) * mw, slot_bytes,
-                         my_bar);
-            mbar_wait_a(my_bar, wpar);
-            wpar ^= 1;
+            if (!(p.flags & 0x2000)) {
+              if (lane == 0) mbar_arrive_expect_tx(&s_wbar[warp], cnt * slot_bytes);
+              if (mine)
+                bulk_g2s_a(my_slots_a + rank * slot_bytes, tiles_b + (n * mh + jc) * mw, slot_bytes,
+                           my_bar);
+              mbar_wait_a(my_bar, wpar);
+              wpar ^= 1;
+            }
             // ---- sample them in lane order
             for (int k = 0; k < cnt; ++k) {
               const int src = __ffs(mask) - 1;

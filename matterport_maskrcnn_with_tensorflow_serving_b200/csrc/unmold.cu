@@ -664,7 +664,11 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   // the warp-specialised kernel keeps a blended tile row in one warp's registers
   // (mw + 2 <= 32 lanes); wider tiles take the generic kernel
   const bool use_v2 = (impl != nullptr && strcmp(impl, "v2") == 0) || mw > 30;
-  if (!use_v2) return launch_expand_ws(prm, sms, max_optin, st);
+  if (!use_v2) {
+    const bool use_v5 = impl != nullptr && strcmp(impl, "v5") == 0;
+    return use_v5 ? launch_expand_ws(prm, sms, max_optin, st)
+                  : launch_expand_ws4(prm, sms, max_optin, st);
+  }
   const size_t smem = static_cast<size_t>(chunk_bytes) +
                       static_cast<size_t>(kEMax) * 2 * mw * sizeof(float) +
                       static_cast<size_t>(kEMax) * sizeof(Entry) +
