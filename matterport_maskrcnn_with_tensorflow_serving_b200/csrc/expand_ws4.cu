@@ -16,9 +16,9 @@ namespace ws4 {
 // mask expand, warp-specialised: ONE persistent CTA per SM, 32 warps
 // =====================================================================================
 //
-//   warps 30,31 producers: fetch work units, list the (box,row) entries of each chunk, issue
+//   warps 29-31 producers: fetch work units, list the (box,row) entries of each chunk, issue
 //                          the 1-D TMA loads of their tile rows, cut spans into units
-//   warps 27-29 store    : when a chunk is complete, one bulk (TMA) store shared -> HBM,
+//   warps 27,28 store    : when a chunk is complete, one bulk (TMA) store shared -> HBM,
 //                          then re-zeroes the buffer (this is the canvas zero fill)
 //   warps 0..26 consumers: kGroups groups of kGroupWarps; a group takes every kGroups-th
 //                          item; a warp takes span units: vertical blend of the two staged

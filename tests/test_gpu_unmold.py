@@ -203,3 +203,52 @@ def test_generic_kernel_path(cuda_device, monkeypatch):
     monkeypatch.setenv("MRX_EXPAND_IMPL", "v2")
     im = synth.make_batch(12, 1, (300, 420), 40, num_classes=6)[0]
     _check_image(im, np.float64)
+
+
+def test_config4_4k_shape_properties(cuda_device):
+    """BASELINE.json config 4 shape: 3840x2160 original, 50 instances (one image here; the
+    batch of 128 shards by image).  Support inside the box, per-instance parity with the
+    oracle on a sample of instances, counts of ones computed on the device."""
+    import torch
+
+    ims = synth.make_batch(55, 2, (2160, 3840), 50, max_instances=50)
+    eng = UnmoldEngine(2, 50, (28, 28), 81)
+    eng.plan([make_geom(im.original_image_shape, im.image_shape, im.window) for im in ims])
+    d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
+    d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
+    eng.enqueue(d_det, d_msk)
+    counts, boxes, cls, scores = eng.fetch_meta()
+    for b, im in enumerate(ims):
+        k = int(counts[b])
+        assert k == 50
+        v = eng.canvas_view(b, k)
+        assert int(v.max()) <= 1
+        per_inst = v.sum(dim=(0, 1), dtype=torch.int64).cpu().numpy()
+        # boxes: upstream's window / affine / denorm arithmetic on the same float32 rows
+        wn = oracle.norm_boxes(np.array(im.window), im.image_shape[:2])
+        shift = np.array([wn[0], wn[1], wn[0], wn[1]])
+        scale = np.array([wn[2] - wn[0], wn[3] - wn[1], wn[2] - wn[0], wn[3] - wn[1]])
+        ref_boxes = oracle.denorm_boxes(np.divide(im.detections[:k, :4] - shift, scale),
+                                        im.original_image_shape[:2])
+        np.testing.assert_array_equal(boxes[b, :k], ref_boxes)
+        for i in range(0, k, 7):
+            y1, x1, y2, x2 = boxes[b, i]
+            sub = v[y1:y2, x1:x2, i].cpu().numpy().view(np.bool_)
+            assert sub.sum() == per_inst[i]                      # nothing outside the box
+            tile = im.mrcnn_mask[i, :, :, int(cls[b, i])].astype(np.float64)
+            rz = oracle.resize(tile, (y2 - y1, x2 - x1))
+            d = sub != (rz >= 0.5)
+            assert not (d & (np.abs(rz - 0.5) > MASK_VALUE_ATOL)).any()
+
+
+def test_config3_coco_batch_ragged(cuda_device):
+    """BASELINE.json config 3 shape: 800x1333 originals, 1-100 instances per image (a batch
+    of 6 here): row size not a multiple of 16 -> flat chunks; exact ints, masks vs oracle."""
+    ims = synth.make_batch(66, 6, (800, 1333), (1, 100))
+    got = api_utils.unmold_detections_batch([item_of(im, np.float32) for im in ims])
+    for im, g in zip(ims, got):
+        rb, rc, rs, rm, rz = oracle_unmold(im, np.float32, return_resized=True)
+        np.testing.assert_array_equal(g[0], rb)
+        np.testing.assert_array_equal(g[1], rc)
+        np.testing.assert_array_equal(g[2], rs)
+        assert compare_masks(g[3], rm, rz, rb)[0] == 0
