@@ -683,13 +683,14 @@ mask_expand_ws_kernel(const ExpandParams p) {
           idx = i0 + 1;   // B[idx], B[idx+1] are the two taps
         }
         unsigned off = static_cast<unsigned>(e.obase + x * it.N);
+#pragma unroll 2
         for (int xs = x0; xs < xend; xs += 32) {   // warp-uniform trip count (shuffles inside)
           const float wx = static_cast<float>(rem) * e.invD;
           const float a = __shfl_sync(0xffffffffu, bl, idx);
           const float bq = __shfl_sync(0xffffffffu, bl, idx + 1);
           const float v = fmaf(wx, bq - a, a);
           if (v >= 0.5f && x < xend && off < ulen)
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(out_addr + off), "r"(1u) : "memory");
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(out_addr + off), "r"(1u));
           x += 32;
           off += ostep;
           rem += e.stepR;
