@@ -334,3 +334,71 @@ class Molder:
             _ptr(u8) if u8 is not None else C.c_void_p(0), N.stream_ptr(stream)),
             "mrx_mold_image")
         return out, u8, window, scale, padding
+
+
+class StreamingUnmolder:
+    """Host-buffer pipeline around UnmoldEngine for a stream of equally-shaped batches:
+    the H2D copy of batch k+1 (own stream, double-buffered device inputs) overlaps the D2H
+    copy of batch k's masks (PCIe is full duplex); results land in double-buffered pinned
+    host memory and are valid after `wait(k)`.
+
+        sm = StreamingUnmolder(engine, geoms)
+        for k, (h_det, h_msk) in enumerate(batches):      # pinned [n,R,6] / [n,R,mh,mw,C]
+            sm.submit(h_det, h_msk)
+            if k: counts, boxes, masks = sm.wait(k - 1)
+    """
+
+    def __init__(self, engine, geoms):
+        torch = _torch()
+        self.eng = engine
+        engine.plan(geoms)
+        n = engine._n_images
+        self.n = n
+        dev = engine.device
+        det_t, msk_t = _torch_dtype(engine.det_dtype), _torch_dtype(engine.mask_dtype)
+        self.d_det = [torch.empty((n, engine.R, 6), dtype=det_t, device=dev) for _ in range(2)]
+        self.d_msk = [torch.empty((n, engine.R, engine.mh, engine.mw, engine.C), dtype=msk_t,
+                                  device=dev) for _ in range(2)]
+        self.total = int(engine._offsets[n])
+        self.h_out = [torch.empty((self.total,), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.h_counts = [torch.empty((n,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.h_boxes = [torch.empty((n, engine.R, 4), dtype=torch.int32).pin_memory()
+                        for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.main_stream = torch.cuda.current_stream(dev)
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self.in_free = [torch.cuda.Event() for _ in range(2)]
+        self.out_done = {}
+        self.k = 0
+        self.h2d_bytes = self.d_det[0].numel() * self.d_det[0].element_size() + \
+            self.d_msk[0].numel() * self.d_msk[0].element_size()
+        self.d2h_bytes = self.total + 4 * (n + 4 * n * engine.R)
+
+    def submit(self, h_det, h_msk):
+        torch = _torch()
+        k, i = self.k, self.k % 2
+        with torch.cuda.stream(self.copy_stream):
+            if k >= 2:
+                self.copy_stream.wait_event(self.in_free[i])     # kernels of batch k-2 read d_*[i]
+            self.d_det[i].copy_(h_det, non_blocking=True)
+            self.d_msk[i].copy_(h_msk, non_blocking=True)
+            self.h2d_done[i].record(self.copy_stream)
+        ms = self.main_stream
+        ms.wait_event(self.h2d_done[i])
+        self.eng.enqueue(self.d_det[i], self.d_msk[i], ms)       # also orders after batch k-1's D2H
+        self.in_free[i].record(ms)
+        self.h_counts[i].copy_(self.eng.d_counts[:self.n], non_blocking=True)
+        self.h_boxes[i].copy_(self.eng.d_boxes[:self.n], non_blocking=True)
+        self.h_out[i].copy_(self.eng.d_canvas[:self.total], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(ms)
+        self.out_done[k] = ev
+        self.k += 1
+        return k
+
+    def wait(self, k):
+        """Block until batch k's results are in pinned host memory; returns
+        (counts [n] int32, boxes [n,R,4] int32, canvas bytes uint8) as torch CPU tensors."""
+        self.out_done.pop(k).synchronize()
+        i = k % 2
+        return self.h_counts[i], self.h_boxes[i], self.h_out[i]

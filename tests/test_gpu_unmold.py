@@ -252,3 +252,42 @@ def test_config3_coco_batch_ragged(cuda_device):
         np.testing.assert_array_equal(g[1], rc)
         np.testing.assert_array_equal(g[2], rs)
         assert compare_masks(g[3], rm, rz, rb)[0] == 0
+
+
+def test_streaming_unmolder_pipeline(cuda_device):
+    """engine.StreamingUnmolder: double-buffered H2D / D2H around the engine gives the same
+    bytes as the plain call, batch after batch."""
+    import torch
+
+    from matterport_maskrcnn_with_tensorflow_serving_b200.engine import StreamingUnmolder
+
+    batches = [synth.make_batch(300 + k, 3, (160, 208), 20, num_classes=5, max_instances=20)
+               for k in range(4)]
+    geoms = [make_geom(im.original_image_shape, im.image_shape, im.window) for im in batches[0]]
+    eng = UnmoldEngine(3, 20, (28, 28), 5)
+    sm = StreamingUnmolder(eng, geoms)
+    pinned = []
+    for ims in batches:
+        h_det = torch.from_numpy(np.stack([im.detections for im in ims])).pin_memory()
+        h_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).pin_memory()
+        pinned.append((h_det, h_msk))
+    tickets = []
+    results = {}
+    for k, (h_det, h_msk) in enumerate(pinned):
+        tickets.append(sm.submit(h_det, h_msk))
+        if k:
+            c, b, o = sm.wait(tickets[k - 1])
+            results[k - 1] = (c.clone(), b.clone(), o.clone())
+    c, b, o = sm.wait(tickets[-1])
+    results[len(pinned) - 1] = (c.clone(), b.clone(), o.clone())
+    for k, ims in enumerate(batches):
+        counts, boxes, out = results[k]
+        for i, im in enumerate(ims):
+            rb, rc, rs, rm, rz = oracle_unmold(im, np.float32, return_resized=True)
+            n = int(counts[i])
+            assert n == rb.shape[0]
+            np.testing.assert_array_equal(boxes[i, :n].numpy(), rb)
+            off = int(eng._offsets[i])
+            H, W = im.original_image_shape[:2]
+            m = out[off:off + H * W * n].numpy().reshape(H, W, n).view(np.bool_)
+            assert compare_masks(m, rm, rz, rb)[0] == 0
