@@ -1,16 +1,20 @@
-// expand_ws.cu -- the hot kernel of api_utils.unmold_detections
+// expand_ws.cu -- generation 5 of the hot kernel (selected with MRX_EXPAND_IMPL=v5; the default
+// is generation 4 in expand_ws4.cu, which is faster this round: 0.79 vs 0.85 ms on config 2).
+// Same job as generation 4 -- the hot kernel of api_utils.unmold_detections
 // (/root/reference/serve.py:147-154): per-instance 28x28 -> box bilinear resize (zero border,
 // half-pixel centres), >= 0.5, paste, np.stack(axis=-1), fused with the canvas zero fill so
 // that HBM sees one write per output byte.
 //
-// One persistent 1024-thread CTA per SM, warp-specialised; hand-offs through mbarriers.
+// One persistent CTA per SM (kWarps warps, see the constants below), warp-specialised;
+// hand-offs through mbarriers.  With the constants of this round: 6 consumer groups x 4
+// warps, 3 store warps, 3 producers.
 //
-//   warps 30,31  producers  fetch work units from a global counter and publish JOB
+//   producers    (highest)  fetch work units from a global counter and publish JOB
 //                           DESCRIPTORS (one per chunk of canvas): geometry only
-//   warps 27-29  store      when a chunk is complete: fence.proxy.async, ONE bulk (TMA) store
+//   store warps             when a chunk is complete: fence.proxy.async, ONE bulk (TMA) store
 //                           of the chunk shared -> HBM, wait_group.read, re-zero the buffer
 //                           (this is the canvas zero fill), hand the buffer back
-//   warps 0-26   consumers  3 groups x 9 warps; a group takes every 3rd job.  Each warp owns a
+//   consumers    (lowest)   kGroups groups; a group takes every kGroups-th job.  Each warp owns a
 //                           slice of the image's boxes: tests them against the job's rows and
 //                           columns (one box per lane), stages the two tile rows each hit
 //                           interpolates between with its own 1-D TMA bulk copy
@@ -28,7 +32,7 @@
 // the same way.
 //
 // Rings in shared memory:
-//   descriptors (kNS)      full[s] (producer -> group)      empty[s] (9 consumer warps -> producer)
+//   descriptors (kNS)      full[s] (producer -> group)      empty[s] (group's warps -> producer)
 //   chunk buffers (kNB)    done[b] (last consumer -> store) free[b]  (store warp -> producer)
 // Tickets number the jobs CTA-wide: ticket t uses descriptor stage t % kNS, chunk buffer
 // t % kNB and consumer group t % kGroups.  Several producers can hold tickets one ring apart
@@ -42,7 +46,7 @@ namespace mrx {
 
 constexpr int kGroups = 6;
 constexpr int kGroupWarps = 4;
-constexpr int kConsumerWarps = kGroups * kGroupWarps;   // warps 0..26
+constexpr int kConsumerWarps = kGroups * kGroupWarps;   // the lowest warp ids
 constexpr int kStoreWarps = 3;                          // store warp j owns buffers b % 3 == j
 constexpr int kProducers = 3;
 constexpr int kWarps = kConsumerWarps + kStoreWarps + kProducers;
