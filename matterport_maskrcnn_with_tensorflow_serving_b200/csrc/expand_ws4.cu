@@ -53,7 +53,7 @@ constexpr int kMaxUnitsPerEntry = kUMax / 32;
 constexpr int kBoxCache = 128;   // per-producer box / aux / active tables
 constexpr int kBandRows = 32;
 constexpr int kFlatGroup = 8;
-constexpr int kMinUnitShift = 2;   // span units are at least 128 columns (4 sampling steps)
+constexpr int kMinUnitShift = 3;   // span units are at least 256 columns (8 sampling steps)
 constexpr int kFirstProducerWarp = kWsWarps - kProducers;   // highest warp ids: favoured by the issue arbiter
 constexpr int kFirstStoreWarp = kFirstProducerWarp - kStoreWarps;
 static_assert(kNS % kGroups == 0 && kNS >= kProducers + 1, "stage ring must interleave the groups");
