@@ -51,7 +51,7 @@ constexpr int kNS = 6;   // item stages: two per consumer group
 constexpr int kUMax = 256;
 constexpr int kMaxUnitsPerEntry = kUMax / 32;
 constexpr int kBoxCache = 128;   // per-producer box / aux / active tables
-constexpr int kBandRows = 32;
+constexpr int kBandRows = 8;
 constexpr int kFlatGroup = 8;
 constexpr int kMinUnitShift = 3;   // span units are at least 256 columns (8 sampling steps)
 constexpr int kFirstProducerWarp = kWsWarps - kProducers;   // highest warp ids: favoured by the issue arbiter
