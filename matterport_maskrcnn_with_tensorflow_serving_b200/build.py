@@ -44,7 +44,7 @@ def _fingerprint():
     for path in [os.path.join(CSRC, s) for s in SOURCES] + HEADERS:
         with open(path, "rb") as f:
             h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("MRX_NVCC_FLAGS", "")).encode())
     return h.hexdigest()
 
 
@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
         with open(STAMP_PATH) as f:
             if f.read().strip() == fp:
                 return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("MRX_NVCC_FLAGS", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
