@@ -31,6 +31,10 @@ struct ExpandParams {
 // Launch the warp-specialised kernel (one persistent CTA per SM).  Returns MRX_OK or an error
 // code with mrx_last_error() set.  Requires mw <= 30.
 int launch_expand_ws(const ExpandParams &prm, int sms, int max_smem_optin, cudaStream_t st);    // gen 5
-int launch_expand_ws4(const ExpandParams &prm, int sms, int max_smem_optin, cudaStream_t st);   // gen 4 (default)
+int launch_expand_ws4(const ExpandParams &prm, int sms, int max_smem_optin, cudaStream_t st);   // gen 4
+// Generation 6 (default): teams of warps build 2-D tiles.  want_buf = upper bound of a team's
+// tile buffer in bytes (0 = as large as fits).  MRX_E_UNSUPPORTED when R does not fit a buffer.
+int launch_expand_team(const ExpandParams &prm, int sms, int max_smem_optin, int want_buf,
+                       cudaStream_t st);
 
 }  // namespace mrx

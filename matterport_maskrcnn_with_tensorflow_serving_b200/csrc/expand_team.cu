@@ -1,0 +1,608 @@
+// expand_team.cu -- mask-expand kernel, generation 6 (the default): 2-D canvas tiles built by
+// TEAMS of warps.  Replaces the producer/consumer/store roles of generations 3-5
+// (expand_ws4.cu, expand_ws.cu) with one role and three named barriers per tile.
+//
+// Why: the store pattern alone (shared memory -> HBM bulk copies of 8 x 6400 B, no box work)
+// writes a B200 at ~7.4 TB/s (tools/store_ceiling.cu), but generation 4 reached 4.6 TB/s: its
+// producer warps -- one dependent instruction stream listing (box,row) entries and issuing a
+// TMA load per entry -- were the critical path.  Here a tile is kTileRows canvas rows high, so
+// a box meets a tile once (not once per row), the horizontal source coordinates of a 32-column
+// block are computed once and reused for every row, and the tile rows a box interpolates between
+// come straight from L1/L2 (the packed tiles of an image are 3136 B each and stay cached).
+//
+//   CTA  = kTeams teams x kTeamWarps warps, one persistent CTA per SM
+//   team = owns ONE tile buffer in shared memory; loops over its tiles (static round robin):
+//            B1 | warp 0: bulk-store the finished tile row by row (cp.async.bulk.global.shared),
+//               |         decode the tile after next, wait until the buffer has been read
+//               | others: cull the boxes of the next tile into the team's entry list
+//            B2 | all   : zero the buffer  (this IS the canvas zero fill)
+//            B3 | all   : items = (entry, 32-column block): vertical blend of the two tile rows
+//               |         into one register per lane, horizontal lerp by two warp shuffles,
+//               |         >= 0.5, st.shared.u8 -- for up to kTileRows rows per item
+//          While one team waits for its buffer to drain, the other teams compute.
+//
+// A tile is P pixels x kTileRows rows of one image: row r is P*N contiguous canvas bytes
+// (N innermost).  When W*N is a multiple of 16 every row segment is 16-byte aligned and is
+// stored by one bulk copy.  Otherwise ("flat" shapes, e.g. W = 1333 with ragged N) each row is
+// placed in shared memory at the same offset mod 16 as its global address, the 16-byte
+// aligned body goes out as a bulk copy and the <= 15 head / tail bytes as byte stores.
+// HBM sees every canvas byte written exactly once either way.
+#include <stdlib.h>
+#include <string.h>
+
+#include "expand.cuh"
+
+namespace mrx {
+
+namespace team {
+
+constexpr int kMaxP = 256;   // tile width limit in pixels (8 column blocks)
+constexpr int kCand = 128;   // boxes tested per cull pass == capacity of the entry list
+
+// One box that meets the tile, with everything about it that is the same for all of its
+// column blocks (written once by the culling lane).
+struct __align__(16) TEntry {
+  int x1, x2;    // box columns
+  int npk;       // n | ra << 16 | rb << 22 : instance, first and one-past-last tile row in the box
+  float invD;    // 1 / (2 * box width)
+  int Dy;        // 2 * box height
+  float invDy;   // 1 / Dy
+  int j0a;       // floor of the vertical source coordinate of tile row ra, in [-1, mh-1]
+  int remya;     // its remainder: (coordinate - j0a) * Dy
+};
+
+struct __align__(16) TJob {
+  const float *tiles_b;
+  const int4 *boxes_b;
+  unsigned char *g0;   // global address of (row y0, pixel x0, instance 0)
+  int valid;
+  int N, H, W;
+  int x0, pw;          // first pixel and width in pixels
+  int y0, kk;          // first row and number of rows
+  int pitch;           // shared-memory distance between tile rows (multiple of 16)
+  unsigned RW;         // canvas row bytes W * N
+  int pad0_, pad1_;
+};
+
+// Tile geometry of an image: tile width in pixels and the shared-memory row pitch.
+// `rowcap` = buffer bytes / tile rows (a multiple of 16).
+__device__ __forceinline__ void tile_geom(int W, int N, int rowcap, int &P, int &pitch) {
+  const unsigned RW = static_cast<unsigned>(W) * N;
+  if ((RW & 15u) == 0u) {
+    // pixel granularity that keeps P*N a multiple of 16: 16 / gcd(N, 16)
+    const int m = 16 / (((N | 16) & -(N | 16)));   // lowest set bit of N|16 == gcd(N,16)
+    int p = (rowcap / N) / m * m;
+    if (p > kMaxP) p = kMaxP;   // a multiple of 16, hence of m
+    if (p < m) p = m;           // the host checks 16 * R * kTileRows <= buffer
+    if (p >= W) p = W;
+    P = p;
+    pitch = p * N;              // multiple of 16 (p multiple of m, or p = W with RW % 16 == 0)
+  } else {
+    int p = (rowcap - 32) / N;
+    if (p > kMaxP) p = kMaxP;
+    if (p < 1) p = 1;
+    if (p >= W) p = W;
+    P = p;
+    pitch = ((p * N + 15) & ~15) + 16;   // room for the alignment shift (<= 15) of a row
+  }
+}
+
+__device__ __forceinline__ int tiles_of(int H, int W, int N, int rowcap, int tile_rows) {
+  if (N <= 0 || H <= 0 || W <= 0) return 0;
+  int P, pitch;
+  tile_geom(W, N, rowcap, P, pitch);
+  return ((W + P - 1) / P) * ((H + tile_rows - 1) / tile_rows);
+}
+
+// ---- phase profile (build with -DMRX_TEAM_PROFILE): per-warp cycle totals of the six phases
+// of a team's tile loop, read back with mrx_debug_team_profile()
+#ifdef MRX_TEAM_PROFILE
+__device__ long long g_team_prof[148 * 32 * 12];
+#define PROF_DECL long long prof_t = clock64(), prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_ADD(k, v) prof_acc[k] += (v);
+#define PROF_NOW clock64()
+#define PROF_MARK(k)                         \
+  {                                          \
+    const long long now_ = clock64();        \
+    prof_acc[k] += now_ - prof_t;            \
+    prof_t = now_;                           \
+  }
+#define PROF_FLUSH                                                                   \
+  if (lane == 0 && blockIdx.x < 148 && warp < 32) {                                  \
+    for (int k_ = 0; k_ < 12; ++k_)                                                  \
+      g_team_prof[(blockIdx.x * 32 + warp) * 12 + k_] = prof_acc[k_];                \
+  }
+#else
+#define PROF_DECL
+#define PROF_MARK(k)
+#define PROF_FLUSH
+#define PROF_ADD(k, v)
+#define PROF_NOW 0
+#endif
+
+__device__ __forceinline__ void team_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int kTeams, int kTeamWarps, int kTileRows>
+__global__ void __launch_bounds__(kTeams * kTeamWarps * 32, 1)
+mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
+  static_assert(kTileRows <= 32 && kTeamWarps >= 3, "one store lane per tile row; cull + decode warps");
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kTeamThreads = kTeamWarps * 32;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int tm = warp / kTeamWarps;            // team
+  const int wt = warp - tm * kTeamWarps;       // warp within the team
+  const int tt = tid - tm * kTeamThreads;      // thread within the team
+  const int mh = p.mh, mw = p.mw;
+  const int rowcap = (buf_bytes / kTileRows) & ~15;
+
+  // ---- carve shared memory: [team buffers][team entry lists][team job descriptors][prefix]
+  unsigned char *s_buf = smem + static_cast<size_t>(tm) * buf_bytes;
+  TEntry *s_ent = reinterpret_cast<TEntry *>(smem + static_cast<size_t>(kTeams) * buf_bytes) + tm * kCand;
+  TJob *s_job = reinterpret_cast<TJob *>(smem + static_cast<size_t>(kTeams) * buf_bytes +
+                                         static_cast<size_t>(kTeams) * kCand * sizeof(TEntry)) + tm * 2;
+  int *s_prefix = reinterpret_cast<int *>(smem + static_cast<size_t>(kTeams) * buf_bytes +
+                                          static_cast<size_t>(kTeams) * kCand * sizeof(TEntry) +
+                                          static_cast<size_t>(kTeams) * 2 * sizeof(TJob));
+  __shared__ int s_total;
+  __shared__ int s_ecount[kTeams][2];
+
+  // ---- tiles per image -> prefix sums (first warp)
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base < p.B; base += 32) {
+      const int b = base + lane;
+      int v = 0;
+      if (b < p.B)
+        v = tiles_of(p.geom[b * MRX_GEOM_INTS + 0], p.geom[b * MRX_GEOM_INTS + 1], p.counts[b], rowcap, kTileRows);
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (b < p.B) s_prefix[b + 1] = carry + incl;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      s_prefix[0] = 0;
+      s_total = carry;
+    }
+  }
+  __syncthreads();
+  const int total = s_total;
+  const int bar_id = 1 + tm;
+  const uint32_t buf_addr = smem_u32(s_buf);
+
+  // decode tile `j` into *out (one thread); cur_b is the caller's search cursor
+  auto decode = [&](int j, int &cur_b, TJob *out) {
+    if (j >= total) {
+      out->valid = 0;
+      return;
+    }
+    while (j >= s_prefix[cur_b + 1]) ++cur_b;
+    const int b = cur_b;
+    const int H = p.geom[b * MRX_GEOM_INTS + 0];
+    const int W = p.geom[b * MRX_GEOM_INTS + 1];
+    const int N = p.counts[b];
+    int P, pitch;
+    tile_geom(W, N, rowcap, P, pitch);
+    const int tiles_x = (W + P - 1) / P;
+    const int local = j - s_prefix[b];
+    const int band = local / tiles_x;
+    const int tx = local - band * tiles_x;
+    const unsigned RW = static_cast<unsigned>(W) * N;
+    out->tiles_b = p.tiles + static_cast<size_t>(b) * p.R * mh * mw;
+    out->boxes_b = p.boxes + static_cast<size_t>(b) * p.R;
+    out->x0 = tx * P;
+    out->pw = min(P, W - tx * P);
+    out->y0 = band * kTileRows;
+    out->kk = min(kTileRows, H - band * kTileRows);
+    out->g0 = p.canvas + p.canvas_off[b] + static_cast<size_t>(band * kTileRows) * RW +
+              static_cast<size_t>(tx * P) * N;
+    out->N = N;
+    out->H = H;
+    out->W = W;
+    out->pitch = pitch;
+    out->RW = RW;
+    out->valid = 1;
+  };
+
+  // cull the boxes [cbase, cbase + kCand) of tile `jb` into the team's entry list
+  auto cull = [&](const TJob &jb, int cslot, int cbase, int w0, int wstep) {
+    for (int c = w0 * 32; c < kCand; c += wstep * 32) {
+      const int n = cbase + c + lane;
+      bool hit = false;
+      int4 bx = make_int4(0, 0, 0, 0);
+      if (n < jb.N) {
+        bx = __ldg(jb.boxes_b + n);
+        const bool sane = bx.x >= 0 && bx.y >= 0 && bx.z <= jb.H && bx.w <= jb.W && bx.z > bx.x &&
+                          bx.w > bx.y;
+        hit = sane && bx.y < jb.x0 + jb.pw && bx.w > jb.x0 && bx.x < jb.y0 + jb.kk && bx.z > jb.y0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (bal != 0u) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&s_ecount[tm][cslot], __popc(bal));
+        slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(bal & ((1u << lane) - 1u));
+        if (hit) {
+          const int bh = bx.z - bx.x;
+          const int ra = max(bx.x, jb.y0) - jb.y0, rb = min(bx.z, jb.y0 + jb.kk) - jb.y0;
+          TEntry e;
+          e.x1 = bx.y;
+          e.x2 = bx.w;
+          e.npk = n | (ra << 16) | (rb << 22);
+          e.invD = __fdiv_rn(1.0f, static_cast<float>(2 * (bx.w - bx.y)));
+          e.Dy = 2 * bh;
+          e.invDy = __fdiv_rn(1.0f, static_cast<float>(2 * bh));
+          {
+            // exact vertical source coordinate of tile row ra: floor and remainder of Ay / Dy
+            const int Ay = mh * (2 * (jb.y0 + ra - bx.x) + 1) - bh;
+            int j0 = __float2int_rd(static_cast<float>(Ay) * e.invDy);
+            int rem = Ay - j0 * e.Dy;
+            if (rem < 0) {
+              --j0;
+              rem += e.Dy;
+            } else if (rem >= e.Dy) {
+              ++j0;
+              rem -= e.Dy;
+            }
+            e.j0a = j0;
+            e.remya = rem;
+          }
+          s_ent[slot] = e;
+          // warm L1 with the tile rows this box interpolates between inside the tile
+          if (!(p.flags & 0x800)) {
+            const float sc = static_cast<float>(mh) * e.invDy * 2.0f;   // mh / bh
+            const int ya = max(bx.x, jb.y0) - bx.x, yb = min(bx.z, jb.y0 + jb.kk) - 1 - bx.x;
+            const int j_lo = max(0, static_cast<int>(floorf((ya + 0.5f) * sc - 0.5f)));
+            const int j_hi = min(mh - 1, static_cast<int>(floorf((yb + 0.5f) * sc - 0.5f)) + 1);
+            const char *t0 = reinterpret_cast<const char *>(jb.tiles_b + static_cast<size_t>(n) * mh * mw);
+            const char *pa = t0 + static_cast<size_t>(j_lo) * mw * 4;
+            const char *pb = t0 + (static_cast<size_t>(j_hi) * mw + mw) * 4 - 4;
+            pa = reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(pa) & ~static_cast<uintptr_t>(127));
+#pragma unroll 1
+            for (int k = 0; k < 8 && pa <= pb; ++k, pa += 128) {
+              if (p.flags & 0x2000) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
+              } else {
+                // a real load whose result is never used: allocates the line in L1 without a
+                // consumer to wait for it
+                unsigned sink;
+                asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(sink) : "l"(pa));
+              }
+            }
+          }
+        }
+      }
+    }
+  };
+
+  // ---- prologue of the pipeline: decode the first two tiles, cull the first
+  // (the team's last warp decodes, its first warp stores, the ones between cull)
+  int cur_b = 0;   // search cursor of decode(); meaningful in the decoding thread only
+  if (wt == kTeamWarps - 1 && lane == 0) {
+    // tiles are handed out by a global counter (reset by mrx_unmold_prologue): box density
+    // varies across the canvas, a static assignment leaves a tail of late teams
+    const int t0 = static_cast<int>(atomicAdd(p.job_counter, 1u));
+    const int t1 = static_cast<int>(atomicAdd(p.job_counter, 1u));
+    decode(t0, cur_b, &s_job[0]);
+    decode(t1, cur_b, &s_job[1]);
+    s_ecount[tm][0] = 0;
+    s_ecount[tm][1] = 0;
+  }
+  team_bar(bar_id, kTeamThreads);
+  if (!s_job[0].valid) return;   // fewer tiles than teams: nothing for this team
+  {
+    // experiment: stagger the teams of an SM (and SMs) so that they do not drain in lockstep
+    const unsigned unit = (static_cast<unsigned>(p.flags) >> 16) & 0xffu;
+    if (unit) {
+      const unsigned ns = (static_cast<unsigned>(tm) * 4u + (blockIdx.x & 3u)) * unit * 32u;
+      const long long t0 = clock64();
+      while (clock64() - t0 < static_cast<long long>(ns) * 2) {}
+    }
+  }
+  cull(s_job[0], 0, 0, wt, kTeamWarps);
+
+  int slot = 0;      // s_job[slot] / s_ecount[tm][slot] belong to the tile being drawn
+  PROF_DECL
+  while (true) {
+    // ================= B2: entry list of this tile complete, buffer drained
+    PROF_MARK(5)
+    team_bar(bar_id, kTeamThreads);
+    PROF_MARK(0)
+    const TJob *jp = &s_job[slot];
+    const int N = jp->N, x0 = jp->x0, pw = jp->pw, y0 = jp->y0, kk = jp->kk, pitch = jp->pitch;
+    const unsigned RW = jp->RW;
+    unsigned char *const g0 = jp->g0;
+    const float *const tiles_b = jp->tiles_b;
+    if (tt == 0) s_ecount[tm][slot ^ 1] = 0;   // the next tile's counter (idle since tile j-1)
+    // canvas zero fill (fixed trip count: predicated stores, no loop bookkeeping)
+    if (!(p.flags & 0x200)) {
+      uint4 *o4 = reinterpret_cast<uint4 *>(s_buf);
+      const int n16 = (kk * pitch) >> 4;
+      constexpr int kMaxZero = (232448 / kTeams / 16 + kTeamThreads - 1) / kTeamThreads;
+#pragma unroll
+      for (int k = 0; k < kMaxZero; ++k) {
+        const int i = tt + k * kTeamThreads;
+        if (i < n16) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    int cbase = 0;
+    PROF_MARK(1)
+    while (true) {
+      // ================= B3: buffer zeroed / entry list of this pass complete
+      team_bar(bar_id, kTeamThreads);
+      PROF_MARK(2)
+      const int E = (p.flags & 0x100) ? 0 : s_ecount[tm][slot];
+      // ---- items: (entry, 32-column block) pairs, item i = entry * nblk + block, dealt round
+      // robin to the team's warps (at N = 100 a tile is one block wide and an item is an entry)
+      const int nblk = (pw + 31) >> 5;
+      const bool lanecol = lane >= 1 && lane <= mw;
+      const int lcol = min(max(lane - 1, 0), mw - 1);
+      const int a0 = static_cast<int>(reinterpret_cast<uintptr_t>(g0) & 15u);
+      const int rw15 = static_cast<int>(RW & 15u);
+      const bool aligned = (a0 | rw15) == 0;   // every tile row starts 16-byte aligned
+      int ei = 0, c = wt;                      // this warp's next item
+      if (nblk == 1) {
+        ei = wt;
+        c = 0;
+      }
+      while (true) {
+        if (nblk == 1) {
+          if (c != 0) {   // c was advanced by kTeamWarps
+            ei += kTeamWarps;
+            c = 0;
+          }
+        } else {
+          while (c >= nblk) {
+            c -= nblk;
+            ++ei;
+          }
+        }
+        if (ei >= E) break;
+        const long long it_t0 = PROF_NOW;
+        const int4 ea = *reinterpret_cast<const int4 *>(&s_ent[ei]);          // x1, x2, npk, invD
+        const int xa = max(ea.x, x0), xb = min(ea.y, x0 + pw);
+        const int xc = x0 + (c << 5);
+        c += kTeamWarps;
+        if (xc + 32 <= xa || xc >= xb) continue;                              // block outside the box
+        const int4 eb = *(reinterpret_cast<const int4 *>(&s_ent[ei]) + 1);    // Dy, invDy, j0a, remya
+        const float invD = __int_as_float(ea.w), invDy = __int_as_float(eb.y);
+        const int Dy = eb.x;
+        const int n = ea.z & 0xffff, ra = (ea.z >> 16) & 63, rb = (ea.z >> 22) & 63;
+        const int x = xc + lane;
+        const bool colvalid = x >= xa && x < xb;
+        // exact horizontal source coordinate of this lane's column: taps B[idx], B[idx+1] of the
+        // zero-padded tile row (lane l holds column l-1), weight wx
+        int idx;
+        float wx;
+        {
+          const int D = 2 * (ea.y - ea.x);
+          const int A = mw * (2 * (x - ea.x) + 1) - (D >> 1);
+          int i0 = __float2int_rd(static_cast<float>(A) * invD);
+          int rem = A - i0 * D;
+          if (rem < 0) {
+            --i0;
+            rem += D;
+          } else if (rem >= D) {
+            ++i0;
+            rem -= D;
+          }
+          idx = i0 + 1;
+          wx = static_cast<float>(rem) * invD;
+        }
+        const float *tp = tiles_b + static_cast<unsigned>(n * mh * mw + lcol);
+        // raw(j): tile row j in lane-column layout (zero outside the tile);
+        // hrow(raw): its horizontal interpolation at this lane's canvas column
+        auto raw = [&](int j) -> float {
+          const float v = __ldg(tp + static_cast<unsigned>(min(max(j, 0), mh - 1) * mw));
+          return (lanecol && j >= 0 && j < mh) ? v : 0.f;
+        };
+        auto hrow = [&](float rv) -> float {
+          const float a = __shfl_sync(0xffffffffu, rv, idx);
+          const float bq = __shfl_sync(0xffffffffu, rv, idx + 1);
+          return fmaf(wx, bq - a, a);
+        };
+        // the bilinear sample is  ht + wy * (hb - ht)  with ht, hb the horizontal interpolations
+        // of source rows jcur, jcur + 1; consecutive canvas rows share them until the source row
+        // advances
+        int jcur = eb.z, remy = eb.w;
+        uint32_t addr = buf_addr + static_cast<uint32_t>(ra * pitch + (x - x0) * N + n);
+        const int cnt = rb - ra;
+        int step = 2 * mh;
+        asm volatile("" : "+r"(step));   // keep it in a register (ptxas re-reads the constant bank per row otherwise)
+        if (aligned && Dy > step && remy + (cnt - 1) * step < 5 * Dy) {
+          // ---- the common case: 16-byte aligned tile rows and a box tall enough that the tile
+          // meets at most 6 of its source rows (jcur .. jcur+5).  Straight-line, branch-free:
+          // all six rows are fetched and interpolated horizontally up front; the canvas rows
+          // then walk a register queue (ht, hb, q2..q5) that shifts by predicate when the source
+          // row advances.  Rows past the box (i >= cnt) are predicated off.
+          const float r0 = raw(jcur), r1 = raw(jcur + 1), r2 = raw(jcur + 2), r3 = raw(jcur + 3),
+                      r4 = raw(jcur + 4), r5 = raw(jcur + 5);
+          const float thr = colvalid ? 0.5f : __int_as_float(0x7f800000);
+          float ht = hrow(r0), hb = hrow(r1), q2 = hrow(r2), q3 = hrow(r3), q4 = hrow(r4), q5 = hrow(r5);
+          float dh = hb - ht;
+          const long long it_t1 = PROF_NOW;
+          PROF_ADD(8, it_t1 - it_t0)
+          PROF_ADD(10, 1)
+          PROF_ADD(11, cnt)
+#pragma unroll
+          for (int i = 0; i < kTileRows; ++i) {
+            const float v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
+            if (v >= thr && i < cnt) asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(1u));
+            addr += static_cast<uint32_t>(pitch);
+            remy += step;
+            const bool adv = remy >= Dy;   // warp-uniform, applied as a predicate
+            remy = adv ? remy - Dy : remy;
+            ht = adv ? hb : ht;
+            hb = adv ? q2 : hb;
+            q2 = adv ? q3 : q2;
+            q3 = adv ? q4 : q3;
+            q4 = adv ? q5 : q4;
+            dh = hb - ht;
+          }
+          PROF_ADD(9, PROF_NOW - it_t1)
+          continue;
+        }
+        float rawn = raw(jcur + 2);
+        float ht = hrow(raw(jcur)), hb = hrow(raw(jcur + 1));
+        float dh = hb - ht;
+        // ---- general case: any box height, any alignment
+        // source-row advance per canvas row: (2*mh) / Dy and remainder
+        int stepQy = 0;
+        if (Dy <= 2 * mh) stepQy = (2 * mh) / Dy;
+        const int stepRy = 2 * mh - stepQy * Dy;
+        int j0 = jcur;
+        int sh = (a0 + ra * rw15) & 15;
+        for (int r = ra; r < rb; ++r) {
+          if (j0 != jcur) {   // warp-uniform
+            if (j0 == jcur + 1) {
+              ht = hb;
+              hb = hrow(rawn);
+            } else {
+              ht = hrow(raw(j0));
+              hb = hrow(raw(j0 + 1));
+            }
+            jcur = j0;
+            rawn = raw(jcur + 2);
+            dh = hb - ht;
+          }
+          const float v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
+          if (v >= 0.5f && colvalid)
+            asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + static_cast<uint32_t>(sh)), "r"(1u));
+          addr += static_cast<uint32_t>(pitch);
+          sh = (sh + rw15) & 15;
+          remy += stepRy;
+          j0 += stepQy;
+          if (remy >= Dy) {
+            remy -= Dy;
+            ++j0;
+          }
+        }
+      }
+      cbase += kCand;
+      if (cbase >= N) break;
+      // more boxes than one pass holds (N > kCand): another pass over the same tile
+      team_bar(bar_id, kTeamThreads);   // everyone is done with the entry list
+      if (tt == 0) s_ecount[tm][slot] = 0;
+      team_bar(bar_id, kTeamThreads);
+      cull(*jp, slot, cbase, wt, kTeamWarps);
+    }
+    PROF_MARK(3)
+    fence_proxy_async_smem();   // this thread's tile bytes -> visible to the bulk copies
+
+    // ================= B1: tile complete
+    team_bar(bar_id, kTeamThreads);
+    PROF_MARK(4)
+    const int nslot = slot ^ 1;
+    const bool more = s_job[nslot].valid != 0;
+    if (wt == 0) {
+      // ---- store the tile: lane r owns row r
+      const bool mine = lane < kk;
+      if (mine && !(p.flags & 0x400)) {
+        unsigned char *g = g0 + static_cast<size_t>(lane) * RW;
+        const int a = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15u);
+        unsigned char *s = s_buf + lane * pitch + a;
+        const int len = pw * N;
+        const int head = min((16 - a) & 15, len);
+        const int body = (len - head) & ~15;
+        const int tail = len - head - body;
+        if (body > 0) {
+          fence_proxy_async_smem();
+          bulk_s2g(g + head, s + head, static_cast<uint32_t>(body));
+          bulk_commit();
+        }
+        for (int i = 0; i < head; ++i) g[i] = s[i];
+        for (int i = 0; i < tail; ++i) g[head + body + i] = s[head + body + i];
+      }
+      __syncwarp();
+      PROF_MARK(6)
+      // ---- the buffer may be re-zeroed once the bulk copies have read it
+      if (mine) {
+        if (more) bulk_wait_read<0>();
+        else bulk_wait_all<0>();
+      }
+    } else if (more) {
+      if (wt == kTeamWarps - 1) {
+        // ---- the descriptor of this tile retires: decode the tile after next into it
+        if (lane == 0) decode(static_cast<int>(atomicAdd(p.job_counter, 1u)), cur_b, &s_job[slot]);
+        __syncwarp();
+        PROF_MARK(7)
+      } else {
+        cull(s_job[nslot], nslot, 0, wt - 1, kTeamWarps - 2);
+      }
+    }
+    if (!more) break;
+    slot = nslot;
+  }
+  PROF_MARK(5)
+  PROF_FLUSH
+}
+
+}  // namespace team
+
+template <int kTeams, int kTeamWarps, int kTileRows>
+static int launch_team_cfg(const ExpandParams &prm, int sms, int max_optin, int want_buf, cudaStream_t st) {
+  using namespace team;
+  const size_t fixed = static_cast<size_t>(kTeams) * kCand * sizeof(TEntry) +
+                       static_cast<size_t>(kTeams) * 2 * sizeof(TJob) +
+                       static_cast<size_t>(prm.B + 1) * sizeof(int) + 256 /* static __shared__ */;
+  MRX_CHECK_SUPPORTED(fixed + static_cast<size_t>(kTeams) * 2048 <= static_cast<size_t>(max_optin),
+                      "mrx_mask_expand: batch of %d images does not fit the scheduler table", prm.B);
+  const int avail = static_cast<int>((static_cast<size_t>(max_optin) - fixed) / kTeams) & ~127;
+  // a tile row must hold 16 pixels of R instances (aligned shapes) / one pixel + alignment shift
+  const int need = (max(16 * prm.R, prm.R + 48) * kTileRows + 127) & ~127;
+  if (need > avail) return MRX_E_UNSUPPORTED;   // caller falls back to the generic kernel
+  int buf = avail;
+  if (want_buf > 0 && want_buf < buf) buf = want_buf & ~127;
+  if (buf < need) buf = need;
+  const size_t smem = static_cast<size_t>(kTeams) * buf + fixed - 256;
+  auto kern = mask_expand_team_kernel<kTeams, kTeamWarps, kTileRows>;
+  MRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  kern<<<sms, kTeams * kTeamWarps * 32, smem, st>>>(prm, buf);
+  MRX_LAUNCH_CHECK("mask_expand_team_kernel");
+  return MRX_OK;
+}
+
+#ifdef MRX_TEAM_PROFILE
+extern "C" int mrx_debug_team_profile(long long *host_dst, int count) {
+  MRX_CUDA(cudaDeviceSynchronize());
+  MRX_CUDA(cudaMemcpyFromSymbol(host_dst, team::g_team_prof, sizeof(long long) * count));
+  return MRX_OK;
+}
+#endif
+
+// MRX_EXPAND_TEAMS="<teams>x<warps>x<rows>" selects one of the compiled shapes (development sweep)
+int launch_expand_team(const ExpandParams &prm, int sms, int max_optin, int want_buf, cudaStream_t st) {
+  int teams = 4, warps = 7, rows = 16;
+  if (const char *e = getenv("MRX_EXPAND_TEAMS")) {
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%dx%dx%d", &a, &b, &c) == 3) {
+      teams = a;
+      warps = b;
+      rows = c;
+    }
+  }
+  if (prm.mw > 30) return MRX_E_UNSUPPORTED;   // caller falls back to the generic kernel
+#define MRX_TEAM_CASE(T, W, R) \
+  if (teams == T && warps == W && rows == R) return launch_team_cfg<T, W, R>(prm, sms, max_optin, want_buf, st)
+  MRX_TEAM_CASE(4, 7, 16);
+  MRX_TEAM_CASE(4, 5, 16);
+  MRX_TEAM_CASE(4, 4, 16);
+  MRX_TEAM_CASE(2, 14, 32);
+  MRX_TEAM_CASE(2, 10, 32);
+  MRX_TEAM_CASE(2, 8, 32);
+  MRX_TEAM_CASE(2, 16, 32);
+  MRX_TEAM_CASE(3, 9, 21);
+  MRX_TEAM_CASE(3, 7, 21);
+#undef MRX_TEAM_CASE
+  set_error("mrx_mask_expand: MRX_EXPAND_TEAMS=%dx%dx%d is not a compiled shape", teams, warps, rows);
+  return MRX_E_INVALID;
+}
+
+}  // namespace mrx

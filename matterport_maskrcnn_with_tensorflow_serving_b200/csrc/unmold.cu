@@ -630,6 +630,7 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   MRX_CHECK_ARG(B >= 0 && B <= MRX_MAX_BATCH && R >= 1, "mrx_mask_expand: bad sizes B=%d R=%d",
                 B, R);
   if (int rc = check_mask_dims(mh, mw)) return rc;
+  const int want_buf = chunk_bytes;   // generation 6: upper bound of a team's tile buffer, 0 = auto
   if (chunk_bytes == 0) chunk_bytes = 25600;
   MRX_CHECK_ARG(chunk_bytes >= 1024 && (chunk_bytes % 16) == 0,
                 "mrx_mask_expand: chunk_bytes %d must be a multiple of 16, >= 1024", chunk_bytes);
@@ -661,13 +662,16 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const char *impl = getenv("MRX_EXPAND_IMPL");
-  // the warp-specialised kernel keeps a blended tile row in one warp's registers
-  // (mw + 2 <= 32 lanes); wider tiles take the generic kernel
-  const bool use_v2 = (impl != nullptr && strcmp(impl, "v2") == 0) || mw > 30;
+  auto is = [&](const char *name) { return impl != nullptr && strcmp(impl, name) == 0; };
+  // generations 4-6 keep a blended tile row in one warp's registers (mw + 2 <= 32 lanes);
+  // wider tiles take the generic kernel
+  bool use_v2 = is("v2") || mw > 30;
   if (!use_v2) {
-    const bool use_v5 = impl != nullptr && strcmp(impl, "v5") == 0;
-    return use_v5 ? launch_expand_ws(prm, sms, max_optin, st)
-                  : launch_expand_ws4(prm, sms, max_optin, st);
+    if (is("v5")) return launch_expand_ws(prm, sms, max_optin, st);
+    if (is("v4")) return launch_expand_ws4(prm, sms, max_optin, st);
+    const int rc = launch_expand_team(prm, sms, max_optin, want_buf, st);
+    if (rc != MRX_E_UNSUPPORTED) return rc;
+    use_v2 = true;   // R too large for the tile buffers: generic kernel
   }
   const size_t smem = static_cast<size_t>(chunk_bytes) +
                       static_cast<size_t>(kEMax) * 2 * mw * sizeof(float) +

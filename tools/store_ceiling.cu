@@ -1,0 +1,177 @@
+// store_ceiling.cu -- developer microbenchmark (not part of the product): how fast can a B200
+// be WRITTEN with the store pattern of mask_expand (shared memory -> HBM bulk copies), without
+// any of the kernel's box work?  Gives the practical ceiling for the kernel's roofline and
+// compares job geometries (one contiguous chunk vs. k row segments of a 2-D tile).
+//
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o /tmp/store_ceiling tools/store_ceiling.cu
+//   ./store_ceiling            (prints one line per pattern)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e = (x);                                                           \
+    if (e != cudaSuccess) {                                                        \
+      printf("%s failed: %s\n", #x, cudaGetErrorString(e));                        \
+      exit(1);                                                                     \
+    }                                                                              \
+  } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// rows x seg bytes per job; row r of job j goes to base + job_off(j) + r * row_stride
+struct P {
+  unsigned char *dst;
+  long long total;      // canvas bytes
+  int seg;              // bytes per row segment (multiple of 16)
+  int rows;             // row segments per job
+  long long row_stride; // distance between the rows of a job
+  int segs_per_row;     // jobs side by side in a row band
+  long long band_bytes; // rows * row_stride
+  int jobs;
+  int nb;               // chunk buffers per warp
+  int zero;             // re-zero the buffer after each store
+  unsigned int *counter;
+};
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) store_kernel(const P p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int job_bytes = p.seg * p.rows;
+  unsigned char *mine = smem + static_cast<size_t>(warp) * p.nb * job_bytes;
+  for (int i = lane; i < (p.nb * job_bytes) / 16; i += 32)
+    reinterpret_cast<uint4 *>(mine)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  int k = 0;
+  while (true) {
+    int j = 0;
+    if (lane == 0) j = static_cast<int>(atomicAdd(p.counter, 1u));
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= p.jobs) break;
+    unsigned char *buf = mine + static_cast<size_t>(k % p.nb) * job_bytes;
+    // the store issued nb jobs ago from this buffer must have been read out
+    if (lane == 0) {
+      if (p.nb == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      else if (p.nb == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      else if (p.nb == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+      else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+    }
+    __syncwarp();
+    if (p.zero) {
+      for (int i = lane; i < job_bytes / 16; i += 32)
+        reinterpret_cast<uint4 *>(buf)[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const int band = j / p.segs_per_row, sg = j % p.segs_per_row;
+      unsigned char *d = p.dst + band * p.band_bytes + static_cast<long long>(sg) * p.seg;
+      for (int r = 0; r < p.rows; ++r)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                         d + r * p.row_stride),
+                     "r"(smem_u32(buf + r * p.seg)), "r"(p.seg)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    ++k;
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__global__ void plain_fill(uint4 *dst, long long n16) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16; i += stride)
+    dst[i] = make_uint4(0, 0, 0, 0);
+}
+
+template <int kWarps>
+static float run(P p, int sms, int iters) {
+  const size_t smem = static_cast<size_t>(kWarps) * p.nb * p.seg * p.rows;
+  if (smem > 227 * 1024) return -1.f;
+  CK(cudaFuncSetAttribute(store_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          static_cast<int>(smem)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e9f;
+  for (int it = 0; it < iters + 2; ++it) {
+    CK(cudaMemsetAsync(p.counter, 0, 4));
+    CK(cudaEventRecord(e0));
+    store_kernel<kWarps><<<sms, kWarps * 32, smem>>>(p);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (it >= 2 && ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  return best;
+}
+
+int main() {
+  const long long H = 1024, W = 1024, N = 100, B = 32;
+  const long long RW = W * N;
+  const long long total = H * RW * B;   // 3.36 GB
+  unsigned char *dst;
+  unsigned int *counter;
+  CK(cudaMalloc(&dst, total));
+  CK(cudaMalloc(&counter, 4));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  const int sms = prop.multiProcessorCount;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float ms;
+  // 1. cudaMemset
+  for (int it = 0; it < 3; ++it) {
+    CK(cudaEventRecord(e0));
+    CK(cudaMemsetAsync(dst, 0, total));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  printf("cudaMemset            : %.4f ms  %.0f GB/s\n", ms, total / ms / 1e6);
+  // 2. plain st.global.v4 grid-stride
+  for (int it = 0; it < 3; ++it) {
+    CK(cudaEventRecord(e0));
+    plain_fill<<<sms * 8, 256>>>(reinterpret_cast<uint4 *>(dst), total / 16);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  printf("plain st.v4 fill      : %.4f ms  %.0f GB/s\n", ms, total / ms / 1e6);
+
+  struct Geo { int seg, rows; };
+  const Geo geos[] = {{25600, 1}, {3200, 8}, {6400, 4}, {1600, 16}, {12800, 2}, {51200, 1}, {6400, 8}, {3200, 16}, {12800, 1}, {1600, 8}};
+  for (const Geo &g : geos) {
+    for (int zero = 0; zero <= 1; ++zero) {
+      for (int nb = 1; nb <= 4; nb *= 2) {
+        P p;
+        p.dst = dst;
+        p.total = total;
+        p.seg = g.seg;
+        p.rows = g.rows;
+        p.row_stride = RW;
+        p.segs_per_row = static_cast<int>(RW / g.seg);
+        p.band_bytes = g.rows * RW;
+        p.jobs = static_cast<int>(total / (static_cast<long long>(g.seg) * g.rows));
+        p.nb = nb;
+        p.zero = zero;
+        p.counter = counter;
+        const float t2 = run<2>(p, sms, 5);
+        const float t4 = run<4>(p, sms, 5);
+        const float t8 = run<8>(p, sms, 5);
+        printf("seg %6d x rows %2d zero %d nb %d : 2 warps %.4f ms (%.0f GB/s) | 4 warps %.4f ms (%.0f GB/s) | 8 warps %.4f ms (%.0f GB/s)\n",
+               g.seg, g.rows, zero, nb, t2, t2 > 0 ? total / t2 / 1e6 : 0.f, t4,
+               t4 > 0 ? total / t4 / 1e6 : 0.f, t8, t8 > 0 ? total / t8 / 1e6 : 0.f);
+      }
+    }
+  }
+  return 0;
+}
