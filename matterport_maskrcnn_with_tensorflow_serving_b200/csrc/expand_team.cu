@@ -254,28 +254,6 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
             e.remya = rem;
           }
           s_ent[slot] = e;
-          // warm L1 with the tile rows this box interpolates between inside the tile
-          if (!(p.flags & 0x800)) {
-            const float sc = static_cast<float>(mh) * e.invDy * 2.0f;   // mh / bh
-            const int ya = max(bx.x, jb.y0) - bx.x, yb = min(bx.z, jb.y0 + jb.kk) - 1 - bx.x;
-            const int j_lo = max(0, static_cast<int>(floorf((ya + 0.5f) * sc - 0.5f)));
-            const int j_hi = min(mh - 1, static_cast<int>(floorf((yb + 0.5f) * sc - 0.5f)) + 1);
-            const char *t0 = reinterpret_cast<const char *>(jb.tiles_b + static_cast<size_t>(n) * mh * mw);
-            const char *pa = t0 + static_cast<size_t>(j_lo) * mw * 4;
-            const char *pb = t0 + (static_cast<size_t>(j_hi) * mw + mw) * 4 - 4;
-            pa = reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(pa) & ~static_cast<uintptr_t>(127));
-#pragma unroll 1
-            for (int k = 0; k < 8 && pa <= pb; ++k, pa += 128) {
-              if (p.flags & 0x2000) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
-              } else {
-                // a real load whose result is never used: allocates the line in L1 without a
-                // consumer to wait for it
-                unsigned sink;
-                asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(sink) : "l"(pa));
-              }
-            }
-          }
         }
       }
     }
@@ -414,15 +392,28 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
         uint32_t addr = buf_addr + static_cast<uint32_t>(ra * pitch + (x - x0) * N + n);
         const int cnt = rb - ra;
         int step = 2 * mh;
-        asm volatile("" : "+r"(step));   // keep it in a register (ptxas re-reads the constant bank per row otherwise)
+        unsigned one = 1u;
+        asm volatile("" : "+r"(step), "+r"(one));   // keep them in registers (ptxas re-reads the constant bank / re-materialises per row otherwise)
         if (aligned && Dy > step && remy + (cnt - 1) * step < 5 * Dy) {
           // ---- the common case: 16-byte aligned tile rows and a box tall enough that the tile
           // meets at most 6 of its source rows (jcur .. jcur+5).  Straight-line, branch-free:
           // all six rows are fetched and interpolated horizontally up front; the canvas rows
           // then walk a register queue (ht, hb, q2..q5) that shifts by predicate when the source
           // row advances.  Rows past the box (i >= cnt) are predicated off.
-          const float r0 = raw(jcur), r1 = raw(jcur + 1), r2 = raw(jcur + 2), r3 = raw(jcur + 3),
-                      r4 = raw(jcur + 4), r5 = raw(jcur + 5);
+          // rows jcur .. jcur+5 of the tile in lane-column layout; row k is real when
+          // 0 <= jcur + k < mh (only k = 0 can be the zero row above the tile: jcur >= -1)
+          const int lim = lanecol ? mh - jcur : 0;   // row k is inside the tile iff k < lim
+          const float *pr = tp + static_cast<unsigned>(max(jcur, 0) * mw);
+          float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f;
+          if (jcur >= 0) {
+            if (0 < lim) r0 = __ldg(pr);
+            pr += mw;
+          }
+          if (1 < lim) r1 = __ldg(pr);
+          if (2 < lim) r2 = __ldg(pr + mw);
+          if (3 < lim) r3 = __ldg(pr + 2 * mw);
+          if (4 < lim) r4 = __ldg(pr + 3 * mw);
+          if (5 < lim) r5 = __ldg(pr + 4 * mw);
           const float thr = colvalid ? 0.5f : __int_as_float(0x7f800000);
           float ht = hrow(r0), hb = hrow(r1), q2 = hrow(r2), q3 = hrow(r3), q4 = hrow(r4), q5 = hrow(r5);
           float dh = hb - ht;
@@ -433,7 +424,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
 #pragma unroll
           for (int i = 0; i < kTileRows; ++i) {
             const float v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
-            if (v >= thr && i < cnt) asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(1u));
+            if (v >= thr && i < cnt) asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(one));
             addr += static_cast<uint32_t>(pitch);
             remy += step;
             const bool adv = remy >= Dy;   // warp-uniform, applied as a predicate
@@ -593,7 +584,8 @@ int launch_expand_team(const ExpandParams &prm, int sms, int max_optin, int want
   if (teams == T && warps == W && rows == R) return launch_team_cfg<T, W, R>(prm, sms, max_optin, want_buf, st)
   MRX_TEAM_CASE(4, 7, 16);
   MRX_TEAM_CASE(4, 5, 16);
-  MRX_TEAM_CASE(4, 4, 16);
+  MRX_TEAM_CASE(4, 6, 16);
+  MRX_TEAM_CASE(4, 8, 16);
   MRX_TEAM_CASE(2, 14, 32);
   MRX_TEAM_CASE(2, 10, 32);
   MRX_TEAM_CASE(2, 8, 32);
