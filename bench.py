@@ -415,7 +415,7 @@ def run_ours(args, rank, world, local_rank):
                        "sharding": f"images over {world} rank(s), no data-path collective",
                        "l2": "per-step working set (813 MB in + 3.36 GB out per GPU) exceeds the "
                              "126 MB L2; no explicit flush",
-                       "chunk_bytes": eng.chunk_bytes or 25600, "seed": SEED},
+                       "tile_buffer_bytes": eng.chunk_bytes or "auto", "seed": SEED},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
@@ -425,7 +425,7 @@ def run_ours(args, rank, world, local_rank):
                             "masks are waited for on the host"},
             "gpu_launches": 3 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": "mask_expand_kernel",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "mask_expand_team_kernel",
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": int(algo_bytes),
                          "peak_source": peak_src, "traffic_source": traffic_src},
             "cpu_baseline": cpu_block,

@@ -108,10 +108,13 @@ int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype,
  * zero fill, zero-border half-pixel bilinear resize of each tile to its box,
  * >= 0.5 threshold and paste, fused so each output byte is written once.
  *   d_canvas_off [B] int64, each a multiple of 16; slot b must hold at least
- *   round_up(H_b*W_b*N_b, 16) bytes (the pad bytes are written as 0).
- *   chunk_bytes: bytes of canvas one CTA builds in shared memory and stores
- *   with one bulk copy; multiple of 16; 0 = library default.
- *   ctas_per_sm: 0 = as many as fit.                                              */
+ *   round_up(H_b*W_b*N_b, 16) bytes (bytes past H_b*W_b*N_b may or may not be written).
+ *   chunk_bytes: upper bound, in bytes, of the canvas tile a team of warps builds in
+ *   shared memory and stores with one bulk copy per tile row (a tile is P pixels x
+ *   10 rows x N instances; it is raised to the minimum that holds 16 pixels of R
+ *   instances per row); multiple of 16, >= 1024; 0 = as large as fits (library default).
+ *   ctas_per_sm: used by the generic kernel only (R too large for the tile buffers, or
+ *   mask tiles wider than 30 columns); 0 = as many as fit.                           */
 int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
                     const int *d_counts, const int *d_geom, const long long *d_canvas_off,
                     unsigned char *d_canvas, int B, int R, int mh, int mw,
@@ -119,8 +122,9 @@ int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_box_a
                     unsigned int *d_job_counter, void *stream);
 
 /* Pre-threshold resized values of one instance (test hook for the stated fp32
- * tolerance): d_out [bh, bw] float32 for box (y1,x1,y2,x2); uses the same device
- * sampling routine as mrx_mask_expand. */
+ * tolerance): d_out [bh, bw] float32 for box (y1,x1,y2,x2); same exact integer source
+ * coordinates and fp32 weights as mrx_mask_expand (which applies the two lerps in the
+ * other order: horizontal first; both stay within the 1e-6 contract). */
 int mrx_resize_tile_f32(const float *d_tile, int mh, int mw, int bh, int bw,
                         float *d_out, void *stream);
 

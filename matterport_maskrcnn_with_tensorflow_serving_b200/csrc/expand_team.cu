@@ -1,24 +1,30 @@
 // expand_team.cu -- mask-expand kernel, generation 6 (the default): 2-D canvas tiles built by
-// TEAMS of warps.  Replaces the producer/consumer/store roles of generations 3-5
-// (expand_ws4.cu, expand_ws.cu) with one role and three named barriers per tile.
+// TEAMS of warps.  Replaces the producer / consumer / store-warp roles of generations 3-5
+// (expand_ws4.cu, expand_ws.cu) with one role per warp and three named barriers per tile.
 //
-// Why: the store pattern alone (shared memory -> HBM bulk copies of 8 x 6400 B, no box work)
+// Why: the store pattern alone (shared memory -> HBM bulk copies of k x 3200 B, no box work)
 // writes a B200 at ~7.4 TB/s (tools/store_ceiling.cu), but generation 4 reached 4.6 TB/s: its
-// producer warps -- one dependent instruction stream listing (box,row) entries and issuing a
-// TMA load per entry -- were the critical path.  Here a tile is kTileRows canvas rows high, so
-// a box meets a tile once (not once per row), the horizontal source coordinates of a 32-column
-// block are computed once and reused for every row, and the tile rows a box interpolates between
-// come straight from L1/L2 (the packed tiles of an image are 3136 B each and stay cached).
+// producer warps -- one dependent instruction stream listing (box,row) entries and issuing a TMA
+// load per entry -- were the critical path.  Here a tile is kTileRows canvas rows high, so a
+// box meets a tile once (not once per row); the horizontal source coordinate of a 32-column
+// block is computed once and reused for every row; the bilinear sample is evaluated as
+//   v = ht + wy * (hb - ht),   ht / hb = horizontal interpolation of source rows j / j+1
+// so that consecutive canvas rows share ht, hb until the source row advances; and the tile rows
+// come straight from L2 (the packed tiles of an image are 3136 B each).
 //
 //   CTA  = kTeams teams x kTeamWarps warps, one persistent CTA per SM
-//   team = owns ONE tile buffer in shared memory; loops over its tiles (static round robin):
-//            B1 | warp 0: bulk-store the finished tile row by row (cp.async.bulk.global.shared),
-//               |         decode the tile after next, wait until the buffer has been read
-//               | others: cull the boxes of the next tile into the team's entry list
-//            B2 | all   : zero the buffer  (this IS the canvas zero fill)
-//            B3 | all   : items = (entry, 32-column block): vertical blend of the two tile rows
-//               |         into one register per lane, horizontal lerp by two warp shuffles,
-//               |         >= 0.5, st.shared.u8 -- for up to kTileRows rows per item
+//   team = owns ONE tile buffer in shared memory and loops over tiles handed out by a global
+//          counter (box density varies over the canvas: a static assignment leaves a tail):
+//            B1 | warp 0   : bulk-store the finished tile, one row per lane
+//               |            (cp.async.bulk.global.shared::cta), wait until the buffer is read
+//               | last warp: fetch + decode the tile after next
+//               | others   : cull the boxes of the next tile into the team's entry list
+//            B2 | all      : zero the buffer  (this IS the canvas zero fill)
+//            B3 | all      : items = (entry, 32-column block), dealt round robin to the warps:
+//               |            fetch up to six tile rows, interpolate them horizontally with two
+//               |            warp shuffles each, then walk the canvas rows: one FFMA, one
+//               |            compare, one st.shared.u8 per row, the (ht, hb) pair advancing
+//               |            through a register queue by predicate -- straight-line code
 //          While one team waits for its buffer to drain, the other teams compute.
 //
 // A tile is P pixels x kTileRows rows of one image: row r is P*N contiguous canvas bytes
@@ -27,6 +33,10 @@
 // placed in shared memory at the same offset mod 16 as its global address, the 16-byte
 // aligned body goes out as a bulk copy and the <= 15 head / tail bytes as byte stores.
 // HBM sees every canvas byte written exactly once either way.
+//
+// Development switches (MRX_EXPAND_FLAGS): 0x100 no items, 0x200 no zero fill, 0x400 no store.
+// MRX_EXPAND_TEAMS=<teams>x<warps>x<rows> picks another compiled shape.  Build with
+// -DMRX_TEAM_PROFILE (MRX_NVCC_FLAGS) for per-phase cycle counts (tools/team_profile.py).
 #include <stdlib.h>
 #include <string.h>
 
@@ -274,15 +284,6 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
   }
   team_bar(bar_id, kTeamThreads);
   if (!s_job[0].valid) return;   // fewer tiles than teams: nothing for this team
-  {
-    // experiment: stagger the teams of an SM (and SMs) so that they do not drain in lockstep
-    const unsigned unit = (static_cast<unsigned>(p.flags) >> 16) & 0xffu;
-    if (unit) {
-      const unsigned ns = (static_cast<unsigned>(tm) * 4u + (blockIdx.x & 3u)) * unit * 32u;
-      const long long t0 = clock64();
-      while (clock64() - t0 < static_cast<long long>(ns) * 2) {}
-    }
-  }
   cull(s_job[0], 0, 0, wt, kTeamWarps);
 
   int slot = 0;      // s_job[slot] / s_ecount[tm][slot] belong to the tile being drawn
@@ -570,7 +571,7 @@ extern "C" int mrx_debug_team_profile(long long *host_dst, int count) {
 
 // MRX_EXPAND_TEAMS="<teams>x<warps>x<rows>" selects one of the compiled shapes (development sweep)
 int launch_expand_team(const ExpandParams &prm, int sms, int max_optin, int want_buf, cudaStream_t st) {
-  int teams = 4, warps = 7, rows = 16;
+  int teams = 6, warps = 5, rows = 10;
   if (const char *e = getenv("MRX_EXPAND_TEAMS")) {
     int a = 0, b = 0, c = 0;
     if (sscanf(e, "%dx%dx%d", &a, &b, &c) == 3) {
@@ -586,6 +587,14 @@ int launch_expand_team(const ExpandParams &prm, int sms, int max_optin, int want
   MRX_TEAM_CASE(4, 5, 16);
   MRX_TEAM_CASE(4, 6, 16);
   MRX_TEAM_CASE(4, 8, 16);
+  MRX_TEAM_CASE(5, 5, 12);
+  MRX_TEAM_CASE(5, 6, 12);
+  MRX_TEAM_CASE(6, 4, 10);
+  MRX_TEAM_CASE(6, 5, 10);
+  MRX_TEAM_CASE(7, 4, 8);
+  MRX_TEAM_CASE(7, 4, 9);
+  MRX_TEAM_CASE(6, 5, 8);
+  MRX_TEAM_CASE(7, 3, 9);
   MRX_TEAM_CASE(2, 14, 32);
   MRX_TEAM_CASE(2, 10, 32);
   MRX_TEAM_CASE(2, 8, 32);

@@ -178,8 +178,20 @@ gather_tiles_kernel(const T *__restrict__ mask, int R, int tile_elems, int C,
   const int src = src_index[o];
   const T *in = mask + (static_cast<size_t>(b) * R + src) * tile_elems * C + cls;
   float *out = tiles + o * tile_elems;
-  for (int p = threadIdx.x; p < tile_elems; p += kGatherThreads)
-    out[p] = static_cast<float>(in[static_cast<size_t>(p) * C]);
+  // every element is its own 32-byte sector (stride C): keep four loads in flight per thread
+  for (int p0 = threadIdx.x; p0 < tile_elems; p0 += 4 * kGatherThreads) {
+    T v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = p0 + k * kGatherThreads;
+      v[k] = (p < tile_elems) ? in[static_cast<size_t>(p) * C] : T(0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = p0 + k * kGatherThreads;
+      if (p < tile_elems) out[p] = static_cast<float>(v[k]);
+    }
+  }
 }
 
 // =====================================================================================

@@ -71,6 +71,23 @@ def test_leading_unit_batch_dim(cuda_device):
     np.testing.assert_array_equal(got[3], ref[3])
 
 
+@pytest.mark.parametrize("R,n", [(160, 160), (160, 131), (320, 300)])
+def test_more_instances_than_one_cull_pass(cuda_device, R, n):
+    """The team kernel culls 128 boxes per pass: N > 128 takes several passes over a tile;
+    R = 320 does not fit its tile buffers at all and must fall back to the generic kernel."""
+    rng = np.random.default_rng(77)
+    im = synth.make_image(rng, (96, 128), n, num_classes=3, max_instances=R)
+    _check_image(im, np.float64)
+
+
+def test_every_box_meets_every_tile(cuda_device):
+    """Adversarial density: 140 nearly canvas-sized boxes, every tile lists all of them."""
+    rng = np.random.default_rng(78)
+    im = synth.make_image(rng, (64, 96), 140, num_classes=3, max_instances=140,
+                          min_box=60, max_box_frac=1.0)
+    _check_image(im, np.float64)
+
+
 def test_small_boxes_downscale(cuda_device):
     # boxes smaller than the 28x28 tile (no anti-aliasing in the reference)
     rng = np.random.default_rng(8)
