@@ -40,13 +40,15 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "expand.cuh"
 
 namespace mrx {
 
 namespace team {
 
-constexpr int kMaxP = 256;   // tile width limit in pixels (8 column blocks)
+constexpr int kMaxP = 2048;   // tile width limit in pixels (64 column blocks; small N only)
 constexpr int kCand = 128;   // boxes tested per cull pass == capacity of the entry list
 
 // One box that meets the tile, with everything about it that is the same for all of its
@@ -395,12 +397,12 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
         int step = 2 * mh;
         unsigned one = 1u;
         asm volatile("" : "+r"(step), "+r"(one));   // keep them in registers (ptxas re-reads the constant bank / re-materialises per row otherwise)
-        if (aligned && Dy > step && remy + (cnt - 1) * step < 5 * Dy) {
-          // ---- the common case: 16-byte aligned tile rows and a box tall enough that the tile
-          // meets at most 6 of its source rows (jcur .. jcur+5).  Straight-line, branch-free:
-          // all six rows are fetched and interpolated horizontally up front; the canvas rows
-          // then walk a register queue (ht, hb, q2..q5) that shifts by predicate when the source
-          // row advances.  Rows past the box (i >= cnt) are predicated off.
+        if (Dy > step && remy + (cnt - 1) * step < 5 * Dy) {
+          // ---- the common case: a box tall enough that the tile meets at most 6 of its source
+          // rows (jcur .. jcur+5).  Straight-line, branch-free: all six rows are fetched and
+          // interpolated horizontally up front; the canvas rows then walk a register queue
+          // (ht, hb, q2..q5) that shifts by predicate when the source row advances.  Rows past
+          // the box (i >= cnt) are predicated off.
           // rows jcur .. jcur+5 of the tile in lane-column layout; row k is real when
           // 0 <= jcur + k < mh (only k = 0 can be the zero row above the tile: jcur >= -1)
           const int lim = lanecol ? mh - jcur : 0;   // row k is inside the tile iff k < lim
@@ -422,21 +424,29 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
           PROF_ADD(8, it_t1 - it_t0)
           PROF_ADD(10, 1)
           PROF_ADD(11, cnt)
+          auto walk = [&](auto aligned_tag) {
+            constexpr bool kAligned = decltype(aligned_tag)::value;
+            int sh = kAligned ? 0 : ((a0 + ra * rw15) & 15);   // row address mod 16 in HBM
 #pragma unroll
-          for (int i = 0; i < kTileRows; ++i) {
-            const float v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
-            if (v >= thr && i < cnt) asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(one));
-            addr += static_cast<uint32_t>(pitch);
-            remy += step;
-            const bool adv = remy >= Dy;   // warp-uniform, applied as a predicate
-            remy = adv ? remy - Dy : remy;
-            ht = adv ? hb : ht;
-            hb = adv ? q2 : hb;
-            q2 = adv ? q3 : q2;
-            q3 = adv ? q4 : q3;
-            q4 = adv ? q5 : q4;
-            dh = hb - ht;
-          }
+            for (int i = 0; i < kTileRows; ++i) {
+              const float v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
+              if (v >= thr && i < cnt)
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + static_cast<uint32_t>(sh)), "r"(one));
+              addr += static_cast<uint32_t>(pitch);
+              if (!kAligned) sh = (sh + rw15) & 15;
+              remy += step;
+              const bool adv = remy >= Dy;   // warp-uniform, applied as a predicate
+              remy = adv ? remy - Dy : remy;
+              ht = adv ? hb : ht;
+              hb = adv ? q2 : hb;
+              q2 = adv ? q3 : q2;
+              q3 = adv ? q4 : q3;
+              q4 = adv ? q5 : q4;
+              dh = hb - ht;
+            }
+          };
+          if (aligned) walk(std::true_type{});
+          else walk(std::false_type{});
           PROF_ADD(9, PROF_NOW - it_t1)
           continue;
         }
