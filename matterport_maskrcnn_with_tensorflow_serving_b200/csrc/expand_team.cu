@@ -85,6 +85,7 @@ __device__ __forceinline__ void tile_geom(int W, int N, int rowcap, int &P, int 
     const int m = 16 / (((N | 16) & -(N | 16)));   // lowest set bit of N|16 == gcd(N,16)
     int p = (rowcap / N) / m * m;
     if (p > kMaxP) p = kMaxP;   // a multiple of 16, hence of m
+    if (p >= 32) p &= ~31;      // whole 32-column blocks (a warp draws 32 columns at a time)
     if (p < m) p = m;           // the host checks 16 * R * kTileRows <= buffer
     if (p >= W) p = W;
     P = p;
@@ -92,6 +93,7 @@ __device__ __forceinline__ void tile_geom(int W, int N, int rowcap, int &P, int 
   } else {
     int p = (rowcap - 32) / N;
     if (p > kMaxP) p = kMaxP;
+    if (p >= 32) p &= ~31;      // whole 32-column blocks
     if (p < 1) p = 1;
     if (p >= W) p = W;
     P = p;
@@ -140,6 +142,7 @@ template <int kTeams, int kTeamWarps, int kTileRows>
 __global__ void __launch_bounds__(kTeams * kTeamWarps * 32, 1)
 mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
   static_assert(kTileRows <= 32 && kTeamWarps >= 3, "one store lane per tile row; cull + decode warps");
+  static_assert(2 * kTeams + 1 <= 16, "two named barriers per team");
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int kTeamThreads = kTeamWarps * 32;
   const int tid = threadIdx.x;
@@ -161,6 +164,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
                                           static_cast<size_t>(kTeams) * 2 * sizeof(TJob));
   __shared__ int s_total;
   __shared__ int s_ecount[kTeams][2];
+  __shared__ unsigned char s_hit[kTeams][kCand];   // box index - cbase of every hit of a cull pass
 
   // ---- tiles per image -> prefix sums (first warp)
   if (warp == 0) {
@@ -223,14 +227,17 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     out->valid = 1;
   };
 
-  // cull the boxes [cbase, cbase + kCand) of tile `jb` into the team's entry list
+  // cull the boxes [cbase, cbase + kCand) of tile `jb` into the team's entry list, by the warps
+  // w0 = 0 .. wstep-1 of the team.  Two steps: every warp tests 32 boxes per trip and appends the
+  // hits to a byte list; after a barrier among the culling warps the per-entry arithmetic (two
+  // divisions, the exact vertical source coordinate) runs once per 32 hits instead of once per
+  // trip that happened to contain a hit.
   auto cull = [&](const TJob &jb, int cslot, int cbase, int w0, int wstep) {
     for (int c = w0 * 32; c < kCand; c += wstep * 32) {
       const int n = cbase + c + lane;
       bool hit = false;
-      int4 bx = make_int4(0, 0, 0, 0);
       if (n < jb.N) {
-        bx = __ldg(jb.boxes_b + n);
+        const int4 bx = __ldg(jb.boxes_b + n);
         const bool sane = bx.x >= 0 && bx.y >= 0 && bx.z <= jb.H && bx.w <= jb.W && bx.z > bx.x &&
                           bx.w > bx.y;
         hit = sane && bx.y < jb.x0 + jb.pw && bx.w > jb.x0 && bx.x < jb.y0 + jb.kk && bx.z > jb.y0;
@@ -240,34 +247,39 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
         int slot = 0;
         if (lane == 0) slot = atomicAdd(&s_ecount[tm][cslot], __popc(bal));
         slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(bal & ((1u << lane) - 1u));
-        if (hit) {
-          const int bh = bx.z - bx.x;
-          const int ra = max(bx.x, jb.y0) - jb.y0, rb = min(bx.z, jb.y0 + jb.kk) - jb.y0;
-          TEntry e;
-          e.x1 = bx.y;
-          e.x2 = bx.w;
-          e.npk = n | (ra << 16) | (rb << 22);
-          e.invD = __fdiv_rn(1.0f, static_cast<float>(2 * (bx.w - bx.y)));
-          e.Dy = 2 * bh;
-          e.invDy = __fdiv_rn(1.0f, static_cast<float>(2 * bh));
-          {
-            // exact vertical source coordinate of tile row ra: floor and remainder of Ay / Dy
-            const int Ay = mh * (2 * (jb.y0 + ra - bx.x) + 1) - bh;
-            int j0 = __float2int_rd(static_cast<float>(Ay) * e.invDy);
-            int rem = Ay - j0 * e.Dy;
-            if (rem < 0) {
-              --j0;
-              rem += e.Dy;
-            } else if (rem >= e.Dy) {
-              ++j0;
-              rem -= e.Dy;
-            }
-            e.j0a = j0;
-            e.remya = rem;
-          }
-          s_ent[slot] = e;
-        }
+        if (hit) s_hit[tm][slot] = static_cast<unsigned char>(c + lane);
       }
+    }
+    team_bar(1 + kTeams + tm, wstep * 32);   // the culling warps only
+    const int E = s_ecount[tm][cslot];
+    for (int h = w0 * 32 + lane; h < E; h += wstep * 32) {
+      const int n = cbase + s_hit[tm][h];
+      const int4 bx = __ldg(jb.boxes_b + n);
+      const int bh = bx.z - bx.x;
+      const int ra = max(bx.x, jb.y0) - jb.y0, rb = min(bx.z, jb.y0 + jb.kk) - jb.y0;
+      TEntry e;
+      e.x1 = bx.y;
+      e.x2 = bx.w;
+      e.npk = n | (ra << 16) | (rb << 22);
+      e.invD = __fdiv_rn(1.0f, static_cast<float>(2 * (bx.w - bx.y)));
+      e.Dy = 2 * bh;
+      e.invDy = __fdiv_rn(1.0f, static_cast<float>(2 * bh));
+      {
+        // exact vertical source coordinate of tile row ra: floor and remainder of Ay / Dy
+        const int Ay = mh * (2 * (jb.y0 + ra - bx.x) + 1) - bh;
+        int j0 = __float2int_rd(static_cast<float>(Ay) * e.invDy);
+        int rem = Ay - j0 * e.Dy;
+        if (rem < 0) {
+          --j0;
+          rem += e.Dy;
+        } else if (rem >= e.Dy) {
+          ++j0;
+          rem -= e.Dy;
+        }
+        e.j0a = j0;
+        e.remya = rem;
+      }
+      s_ent[h] = e;
     }
   };
 
@@ -503,23 +515,37 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     const int nslot = slot ^ 1;
     const bool more = s_job[nslot].valid != 0;
     if (wt == 0) {
-      // ---- store the tile: lane r owns row r
+      // ---- store the tile: lane r owns the bulk copy of row r (its 16-byte aligned body)
       const bool mine = lane < kk;
+      const int len = pw * N;
       if (mine && !(p.flags & 0x400)) {
         unsigned char *g = g0 + static_cast<size_t>(lane) * RW;
         const int a = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15u);
         unsigned char *s = s_buf + lane * pitch + a;
-        const int len = pw * N;
         const int head = min((16 - a) & 15, len);
         const int body = (len - head) & ~15;
-        const int tail = len - head - body;
         if (body > 0) {
           fence_proxy_async_smem();
           bulk_s2g(g + head, s + head, static_cast<uint32_t>(body));
           bulk_commit();
         }
-        for (int i = 0; i < head; ++i) g[i] = s[i];
-        for (int i = 0; i < tail; ++i) g[head + body + i] = s[head + body + i];
+      }
+      // ---- unaligned shapes: the <= 15 head and <= 15 tail bytes of every row, one byte per
+      // lane (generic-proxy copies; the bulk copies above only read the buffer)
+      if (((reinterpret_cast<uintptr_t>(g0) | RW | static_cast<unsigned>(len)) & 15u) != 0u &&
+          !(p.flags & 0x400)) {
+        for (int r = 0; r < kk; ++r) {
+          unsigned char *g = g0 + static_cast<size_t>(r) * RW;
+          const int a = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15u);
+          const unsigned char *s = s_buf + r * pitch + a;
+          const int head = min((16 - a) & 15, len);
+          const int body = (len - head) & ~15;
+          const int tail = len - head - body;
+          if (lane < head + tail) {
+            const int o = lane < head ? lane : body + lane;   // head + body + (lane - head)
+            g[o] = s[o];
+          }
+        }
       }
       __syncwarp();
       PROF_MARK(6)
@@ -550,9 +576,10 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
 template <int kTeams, int kTeamWarps, int kTileRows>
 static int launch_team_cfg(const ExpandParams &prm, int sms, int max_optin, int want_buf, cudaStream_t st) {
   using namespace team;
+  constexpr size_t kStatic = 256 + static_cast<size_t>(kTeams) * kCand;   // static __shared__ of the kernel
   const size_t fixed = static_cast<size_t>(kTeams) * kCand * sizeof(TEntry) +
                        static_cast<size_t>(kTeams) * 2 * sizeof(TJob) +
-                       static_cast<size_t>(prm.B + 1) * sizeof(int) + 256 /* static __shared__ */;
+                       static_cast<size_t>(prm.B + 1) * sizeof(int) + kStatic;
   MRX_CHECK_SUPPORTED(fixed + static_cast<size_t>(kTeams) * 2048 <= static_cast<size_t>(max_optin),
                       "mrx_mask_expand: batch of %d images does not fit the scheduler table", prm.B);
   const int avail = static_cast<int>((static_cast<size_t>(max_optin) - fixed) / kTeams) & ~127;
@@ -562,7 +589,7 @@ static int launch_team_cfg(const ExpandParams &prm, int sms, int max_optin, int 
   int buf = avail;
   if (want_buf > 0 && want_buf < buf) buf = want_buf & ~127;
   if (buf < need) buf = need;
-  const size_t smem = static_cast<size_t>(kTeams) * buf + fixed - 256;
+  const size_t smem = static_cast<size_t>(kTeams) * buf + fixed - kStatic;
   auto kern = mask_expand_team_kernel<kTeams, kTeamWarps, kTileRows>;
   MRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
