@@ -194,6 +194,13 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
   const uint32_t buf_addr = smem_u32(s_buf);
 
   // decode tile `j` into *out (one thread); cur_b is the caller's search cursor
+  // (per-image constants live in shared memory: registers would cost every thread)
+  struct DecodeCache {
+    unsigned char *canvas;
+    int b, H, W, N, P, pitch, tx, pad_;
+  };
+  __shared__ DecodeCache s_dc[kTeams];
+  DecodeCache &dc = s_dc[tm];
   auto decode = [&](int j, int &cur_b, TJob *out) {
     if (j >= total) {
       out->valid = 0;
@@ -201,12 +208,19 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     }
     while (j >= s_prefix[cur_b + 1]) ++cur_b;
     const int b = cur_b;
-    const int H = p.geom[b * MRX_GEOM_INTS + 0];
-    const int W = p.geom[b * MRX_GEOM_INTS + 1];
-    const int N = p.counts[b];
-    int P, pitch;
-    tile_geom(W, N, rowcap, P, pitch);
-    const int tiles_x = (W + P - 1) / P;
+    if (b != dc.b) {   // per-image constants (divisions), kept by the decoding thread
+      dc.b = b;
+      dc.H = p.geom[b * MRX_GEOM_INTS + 0];
+      dc.W = p.geom[b * MRX_GEOM_INTS + 1];
+      dc.N = p.counts[b];
+      int P_, pitch_;
+      tile_geom(dc.W, dc.N, rowcap, P_, pitch_);
+      dc.P = P_;
+      dc.pitch = pitch_;
+      dc.tx = (dc.W + P_ - 1) / P_;
+      dc.canvas = p.canvas + p.canvas_off[b];
+    }
+    const int H = dc.H, W = dc.W, N = dc.N, P = dc.P, pitch = dc.pitch, tiles_x = dc.tx;
     const int local = j - s_prefix[b];
     const int band = local / tiles_x;
     const int tx = local - band * tiles_x;
@@ -217,7 +231,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     out->pw = min(P, W - tx * P);
     out->y0 = band * kTileRows;
     out->kk = min(kTileRows, H - band * kTileRows);
-    out->g0 = p.canvas + p.canvas_off[b] + static_cast<size_t>(band * kTileRows) * RW +
+    out->g0 = dc.canvas + static_cast<size_t>(band * kTileRows) * RW +
               static_cast<size_t>(tx * P) * N;
     out->N = N;
     out->H = H;
@@ -291,6 +305,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     // varies across the canvas, a static assignment leaves a tail of late teams
     const int t0 = static_cast<int>(atomicAdd(p.job_counter, 1u));
     const int t1 = static_cast<int>(atomicAdd(p.job_counter, 1u));
+    dc.b = -1;
     decode(t0, cur_b, &s_job[0]);
     decode(t1, cur_b, &s_job[1]);
     s_ecount[tm][0] = 0;
@@ -576,7 +591,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
 template <int kTeams, int kTeamWarps, int kTileRows>
 static int launch_team_cfg(const ExpandParams &prm, int sms, int max_optin, int want_buf, cudaStream_t st) {
   using namespace team;
-  constexpr size_t kStatic = 256 + static_cast<size_t>(kTeams) * kCand;   // static __shared__ of the kernel
+  constexpr size_t kStatic = 256 + static_cast<size_t>(kTeams) * (kCand + 48);   // static __shared__ of the kernel
   const size_t fixed = static_cast<size_t>(kTeams) * kCand * sizeof(TEntry) +
                        static_cast<size_t>(kTeams) * 2 * sizeof(TJob) +
                        static_cast<size_t>(prm.B + 1) * sizeof(int) + kStatic;

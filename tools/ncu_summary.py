@@ -1,13 +1,16 @@
 """Summarise an .ncu-rep (raw + source pages) for one kernel: key metrics, stall mix,
-instruction hot spots.  Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep"""
+instruction hot spots.  Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep [lo hi]
+NCU_KERNEL=<regex> picks the kernel when the report holds several."""
 import csv
 import io
+import os
 import subprocess
 import sys
 
 
 def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    sel = ["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []
+    out = subprocess.run(["ncu", "-i", rep] + sel + ["--page", name, "--csv"], capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
