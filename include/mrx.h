@@ -11,6 +11,7 @@
  *   mrx_mask_expand        <- per-instance unmold_mask + np.stack(axis=-1)(same call)
  *   mrx_cv2_resize_u8c3    <- cv2.resize(img, (S, S))                     serve.py:88-89
  *   mrx_mold_image         <- resize_image + mold_image                   serve.py:91-98
+ *   mrx_composite_masks    <- visualize.display_instances (mask overlay)  serve.py:160-169
  *
  * Conventions
  *   - every pointer named d_* is DEVICE memory owned by the caller (the Python
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MRX_ABI_VERSION 2
+#define MRX_ABI_VERSION 3
 
 #define MRX_OK              0
 #define MRX_E_INVALID      -1   /* bad argument (null pointer, size out of range) */
@@ -145,6 +146,23 @@ int mrx_mold_image(const unsigned char *d_src, int src_h, int src_w,
                    int new_h, int new_w, int top, int left, int out_h, int out_w,
                    const double *mean_pixel /* host, 3 */, int out_dtype,
                    void *d_out, unsigned char *d_molded_u8, void *stream);
+
+/* ---------------------------------------------------------------- compositing (8f) */
+/* Mask part of visualize.display_instances(img, boxes, masks, ...) (serve.py:160-169), on
+ * the canvas mrx_mask_expand wrote: for every image b, per instance i in order (skipped when
+ * its box is all zeros), per channel c,
+ *     v = uint32( float64(v) * one_minus_alpha + blend[b][i][c] )      where mask[.,.,i] == 1
+ * starting from the uint8 image and ending with astype(uint8).
+ *   d_images / d_out: uint8 H_b x W_b x 3 images of the batch, image b at byte offset
+ *   d_image_off[b] (int64) in both;  d_blend [B,R,3] float64 = alpha * color[c] * 255,
+ *   evaluated by the caller in float64 in that order;  d_boxes [B,R,4] as written by
+ *   mrx_unmold_prologue;  max_pixels = max_b H_b * W_b (grid sizing). */
+int mrx_composite_masks(const unsigned char *d_canvas, const long long *d_canvas_off,
+                        const int *d_counts, const int *d_geom, const int *d_boxes,
+                        const unsigned char *d_images, const long long *d_image_off,
+                        const double *d_blend, double one_minus_alpha,
+                        unsigned char *d_out, int B, int R, long long max_pixels,
+                        void *stream);
 
 #ifdef __cplusplus
 }

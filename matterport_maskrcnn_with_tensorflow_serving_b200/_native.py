@@ -21,7 +21,7 @@ MRX_ST_CLASS_RANGE = 1
 MRX_ST_BOX_RANGE = 2
 MRX_GEOM_INTS = 8
 MRX_MAX_BATCH = 4096
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class MrxError(RuntimeError):
@@ -46,6 +46,8 @@ SIGNATURES = {
     "mrx_resize_tile_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "mrx_cv2_resize_u8c3": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "mrx_mold_image": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _dp, _i, _vp, _vp, _vp]),
+    "mrx_composite_masks": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _i, _i,
+                                 C.c_longlong, _vp]),
 }
 
 _lib = None

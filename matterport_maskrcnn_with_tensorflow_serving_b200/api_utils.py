@@ -122,6 +122,46 @@ def unmold_detections_batch(items):
     return out
 
 
+def unmold_overlay_batch(items, images, colors=None, alpha=0.5):
+    """`unmold_detections` followed by the mask overlay of `visualize.display_instances`
+    (serve.py:147-169) without moving the masks to the host: the [H,W,N] canvases stay on
+    the device, only boxes, class ids, scores and the blended uint8 images come back.
+
+    items as for `unmold_detections_batch`; images: the original uint8 HxWx3 images;
+    colors: RGB triples (shared list, or one list per image; default: `random_colors(R)`).
+    Returns a list of (boxes, class_ids, scores, overlay_uint8)."""
+    import torch
+
+    from . import visualize
+
+    N.require_cuda()
+    if len(items) == 0:
+        return []
+    dets, masks, geoms = [], [], []
+    for det, msk, osh, ish, win in items:
+        d, m = _squeeze_inputs(det, msk)
+        dets.append(d)
+        masks.append(m)
+        geoms.append(make_geom(osh, ish, win))
+    R, (mh, mw, Cc) = dets[0].shape[0], masks[0].shape[1:]
+    n = len(items)
+    eng = _engine_for(n, R, mh, mw, Cc, dets[0].dtype, masks[0].dtype)
+    eng.plan(geoms)
+    d_det = torch.from_numpy(np.stack(dets)).to(eng.device)
+    d_msk = torch.from_numpy(np.stack(masks)).to(eng.device)
+    eng.enqueue(d_det, d_msk)
+    if colors is None:
+        colors = visualize.random_colors(R)
+    overlays = visualize.composite_batch(eng, images, colors, alpha)
+    counts, boxes, class_ids, scores = eng.fetch_meta()
+    out = []
+    for b in range(n):
+        k = int(counts[b])
+        out.append((boxes[b, :k].copy(), class_ids[b, :k].copy(), scores[b, :k].copy(),
+                    overlays[b].cpu().numpy()))
+    return out
+
+
 def unmold_detections(detections, mrcnn_mask, original_image_shape, image_shape, window):
     """Reformat one image's detections from the molded image back to the original image.
 

@@ -608,6 +608,9 @@ static int launch_team_cfg(const ExpandParams &prm, int sms, int max_optin, int 
   auto kern = mask_expand_team_kernel<kTeams, kTeamWarps, kTileRows>;
   MRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
+  // the tile counter starts at zero for every launch (stream-ordered; mrx_unmold_prologue
+  // also resets it, but the kernel must not depend on having been preceded by it)
+  MRX_CUDA(cudaMemsetAsync(prm.job_counter, 0, sizeof(unsigned int), st));
   kern<<<sms, kTeams * kTeamWarps * 32, smem, st>>>(prm, buf);
   MRX_LAUNCH_CHECK("mask_expand_team_kernel");
   return MRX_OK;

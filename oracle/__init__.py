@@ -36,4 +36,7 @@ from .mrcnn_oracle import (  # noqa: F401
     mold_image,
     compose_image_meta,
     preprocess_input,
+    random_colors,
+    apply_mask,
+    composite_instances,
 )

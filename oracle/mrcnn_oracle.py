@@ -353,3 +353,48 @@ def preprocess_input(img, img_size=640, config=OracleConfig):
     anchors = get_anchors(molded_image.shape, config)
 
     return molded_image, image_meta, anchors, window
+
+
+# =====================================================================================
+# mask compositing of visualize.display_instances (serve.py:160-169)  -- SURVEY.md 8f rank 2
+# =====================================================================================
+def random_colors(N, bright=True, rng=None):
+    """[UPSTREAM mrcnn/visualize.py random_colors] N visually distinct colours: evenly
+    spaced hues in HSV converted to RGB floats in [0,1], then shuffled.  Upstream shuffles
+    with the global `random` module (not reproducible); pass `rng` (a `random.Random`) to
+    make the order reproducible -- the VALUES are the upstream ones."""
+    import colorsys
+    import random as _random
+
+    brightness = 1.0 if bright else 0.7
+    hsv = [(i / N, 1, brightness) for i in range(N)]
+    colors = list(map(lambda c: colorsys.hsv_to_rgb(*c), hsv))
+    (rng or _random).shuffle(colors)
+    return colors
+
+
+def apply_mask(image, mask, color, alpha=0.5):
+    """[UPSTREAM mrcnn/visualize.py apply_mask] blend `color` into `image` where mask == 1.
+    `image` is the uint32 working copy display_instances makes; NumPy evaluates the blend in
+    float64 and the assignment back into the uint32 array truncates."""
+    for c in range(3):
+        image[:, :, c] = np.where(mask == 1,
+                                  image[:, :, c] * (1 - alpha) + alpha * color[c] * 255,
+                                  image[:, :, c])
+    return image
+
+
+def composite_instances(image, boxes, masks, colors, alpha=0.5):
+    """[REF] serve.py:160-169 calls visualize.display_instances(img, boxes, masks, ...);
+    [UPSTREAM] the mask part of its body: masked_image = image.astype(uint32).copy(); for
+    each instance in order, skip it when its box is all zeros, else apply_mask; the figure
+    shows masked_image.astype(uint8).  (Boxes, captions and contour polygons are matplotlib
+    artists drawn on top: not part of this function.)  Returns the uint8 H x W x 3 image."""
+    N = boxes.shape[0]
+    assert masks.shape[-1] == N and len(colors) >= N
+    masked_image = image.astype(np.uint32).copy()
+    for i in range(N):
+        if not np.any(boxes[i]):
+            continue
+        masked_image = apply_mask(masked_image, masks[:, :, i], colors[i], alpha)
+    return masked_image.astype(np.uint8)

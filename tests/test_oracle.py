@@ -181,3 +181,23 @@ def test_preprocess_input_shapes():
     assert molded.shape == (1024, 1024, 3) and molded.dtype == np.float64
     assert window == (112, 112, 912, 912)         # 640x640 -> scale 800/640 -> 800x800, centred in 1024
     assert meta.shape == (12 + 81,) and anchors.shape == (261888, 4)
+
+
+def test_composite_known_answers():
+    """apply_mask arithmetic (upstream visualize.py): float64 blend, truncating uint32 store,
+    instances applied in order, all-zero boxes skipped."""
+    image = np.full((2, 2, 3), 100, dtype=np.uint8)
+    masks = np.zeros((2, 2, 3), dtype=bool)
+    masks[0, 0, 0] = masks[0, 0, 2] = True      # pixel (0,0): instances 0 and 2
+    masks[1, 1, 1] = True                       # pixel (1,1): instance 1, whose box is all zeros
+    boxes = np.array([[0, 0, 2, 2], [0, 0, 0, 0], [0, 0, 1, 1]])
+    colors = [(1.0, 0.0, 0.5), (1.0, 1.0, 1.0), (0.0, 1.0, 0.25)]
+    out = oracle.composite_instances(image, boxes, masks, colors, alpha=0.5)
+    assert out.dtype == np.uint8
+    # instance 0: 100*0.5 + 0.5*c*255 -> (177.5, 50, 113.75) -> (177, 50, 113)
+    # instance 2 on top: (177*0.5 + 0, 50*0.5 + 127.5, 113*0.5 + 31.875) -> (88, 152, 88)
+    assert out[0, 0].tolist() == [88, 152, 88]
+    assert out[1, 1].tolist() == [100, 100, 100]    # skipped instance
+    assert out[0, 1].tolist() == [100, 100, 100]
+    assert len(oracle.random_colors(7)) == 7 and oracle.random_colors(4)[0] in [
+        (1.0, 0.0, 0.0), (0.5, 1.0, 0.0), (0.0, 1.0, 1.0), (0.5, 0.0, 1.0)]
