@@ -55,7 +55,17 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
     const int n16 = (npx * N + 15) >> 4;
     const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
     uint4 *d4 = reinterpret_cast<uint4 *>(s_can);
-    for (int i = t; i < n16; i += kCompThreads) d4[i] = __ldg(s4 + i);
+    // four independent 16-byte loads in flight per thread
+    int i = t;
+    for (; i + 3 * kCompThreads < n16; i += 4 * kCompThreads) {
+      const uint4 a0 = __ldg(s4 + i), a1 = __ldg(s4 + i + kCompThreads),
+                  a2 = __ldg(s4 + i + 2 * kCompThreads), a3 = __ldg(s4 + i + 3 * kCompThreads);
+      d4[i] = a0;
+      d4[i + kCompThreads] = a1;
+      d4[i + 2 * kCompThreads] = a2;
+      d4[i + 3 * kCompThreads] = a3;
+    }
+    for (; i < n16; i += kCompThreads) d4[i] = __ldg(s4 + i);
   }
   __syncthreads();
   if (t >= npx) return;
@@ -71,15 +81,28 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   };
   const unsigned char *mp = s_can + static_cast<size_t>(t) * N;
   if ((N & 3) == 0) {
+    // ~3 % of the bytes are set: test five words (20 instances) with one OR before looking
+    // at any of them
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mp);
-    for (int k = 0; k < (N >> 2); ++k) {
-      const uint32_t w = mw[k];
-      if (w == 0u) continue;
+    const int nw = N >> 2;
+    auto word = [&](int k, uint32_t w) {
+      if (w == 0u) return;
       if (w & 0x000000ffu) apply(4 * k);
       if (w & 0x0000ff00u) apply(4 * k + 1);
       if (w & 0x00ff0000u) apply(4 * k + 2);
       if (w & 0xff000000u) apply(4 * k + 3);
+    };
+    int k = 0;
+    for (; k + 5 <= nw; k += 5) {
+      const uint32_t w0 = mw[k], w1 = mw[k + 1], w2 = mw[k + 2], w3 = mw[k + 3], w4 = mw[k + 4];
+      if ((w0 | w1 | w2 | w3 | w4) == 0u) continue;
+      word(k, w0);
+      word(k + 1, w1);
+      word(k + 2, w2);
+      word(k + 3, w3);
+      word(k + 4, w4);
     }
+    for (; k < nw; ++k) word(k, mw[k]);
   } else {
     for (int i = 0; i < N; ++i)
       if (mp[i]) apply(i);
