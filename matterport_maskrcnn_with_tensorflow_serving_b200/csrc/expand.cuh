@@ -1,5 +1,6 @@
 // expand.cuh -- shared declarations of the mask-expand kernels (csrc/unmold.cu: generic
-// kernel + C ABI; csrc/expand_ws.cu: warp-specialised kernel).
+// kernel + C ABI; csrc/expand_team.cu: the default team kernel; csrc/expand_ws4.cu: the
+// warp-specialised generation 4).
 #pragma once
 
 #include "common.cuh"
@@ -30,7 +31,6 @@ struct ExpandParams {
 
 // Launch the warp-specialised kernel (one persistent CTA per SM).  Returns MRX_OK or an error
 // code with mrx_last_error() set.  Requires mw <= 30.
-int launch_expand_ws(const ExpandParams &prm, int sms, int max_smem_optin, cudaStream_t st);    // gen 5
 int launch_expand_ws4(const ExpandParams &prm, int sms, int max_smem_optin, cudaStream_t st);   // gen 4
 // Generation 6 (default): teams of warps build 2-D tiles.  want_buf = upper bound of a team's
 // tile buffer in bytes (0 = as large as fits).  MRX_E_UNSUPPORTED when R does not fit a buffer.

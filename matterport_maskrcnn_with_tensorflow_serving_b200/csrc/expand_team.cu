@@ -1,6 +1,6 @@
 // expand_team.cu -- mask-expand kernel, generation 6 (the default): 2-D canvas tiles built by
 // TEAMS of warps.  Replaces the producer / consumer / store-warp roles of generations 3-5
-// (expand_ws4.cu, expand_ws.cu) with one role per warp and three named barriers per tile.
+// (expand_ws4.cu; generation 5 was dropped) with one role per warp and three named barriers per tile.
 //
 // Why: the store pattern alone (shared memory -> HBM bulk copies of k x 3200 B, no box work)
 // writes a B200 at ~7.4 TB/s (tools/store_ceiling.cu), but generation 4 reached 4.6 TB/s: its

@@ -693,7 +693,6 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   // wider tiles take the generic kernel
   bool use_v2 = is("v2") || mw > 30;
   if (!use_v2) {
-    if (is("v5")) return launch_expand_ws(prm, sms, max_optin, st);
     if (is("v4")) return launch_expand_ws4(prm, sms, max_optin, st);
     const int rc = launch_expand_team(prm, sms, max_optin, want_buf, st);
     if (rc != MRX_E_UNSUPPORTED) return rc;
