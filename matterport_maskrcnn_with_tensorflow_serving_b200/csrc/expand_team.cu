@@ -434,6 +434,9 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
           // 0 <= jcur + k < mh (only k = 0 can be the zero row above the tile: jcur >= -1)
           const int lim = lanecol ? mh - jcur : 0;   // row k is inside the tile iff k < lim
           const float *pr = tp + static_cast<unsigned>(max(jcur, 0) * mw);
+          // most boxes are tall enough that the tile meets only jcur .. jcur+3 (at most two
+          // advances): fetch and interpolate rows 4 and 5 only when they can be reached
+          const bool deep = remy + (cnt - 1) * step >= 3 * Dy;   // warp-uniform
           float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f;
           if (jcur >= 0) {
             if (0 < lim) r0 = __ldg(pr);
@@ -442,17 +445,23 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
           if (1 < lim) r1 = __ldg(pr);
           if (2 < lim) r2 = __ldg(pr + mw);
           if (3 < lim) r3 = __ldg(pr + 2 * mw);
-          if (4 < lim) r4 = __ldg(pr + 3 * mw);
-          if (5 < lim) r5 = __ldg(pr + 4 * mw);
+          if (deep && 4 < lim) r4 = __ldg(pr + 3 * mw);
+          if (deep && 5 < lim) r5 = __ldg(pr + 4 * mw);
           const float thr = colvalid ? 0.5f : __int_as_float(0x7f800000);
-          float ht = hrow(r0), hb = hrow(r1), q2 = hrow(r2), q3 = hrow(r3), q4 = hrow(r4), q5 = hrow(r5);
+          float ht = hrow(r0), hb = hrow(r1), q2 = hrow(r2), q3 = hrow(r3);
           float dh = hb - ht;
           const long long it_t1 = PROF_NOW;
           PROF_ADD(8, it_t1 - it_t0)
           PROF_ADD(10, 1)
           PROF_ADD(11, cnt)
-          auto walk = [&](auto aligned_tag) {
+          auto walk = [&](auto aligned_tag, auto deep_tag) {
             constexpr bool kAligned = decltype(aligned_tag)::value;
+            constexpr bool kDeep = decltype(deep_tag)::value;
+            float q4 = 0.f, q5 = 0.f;
+            if (kDeep) {
+              q4 = hrow(r4);
+              q5 = hrow(r5);
+            }
             int sh = kAligned ? 0 : ((a0 + ra * rw15) & 15);   // row address mod 16 in HBM
 #pragma unroll
             for (int i = 0; i < kTileRows; ++i) {
@@ -467,13 +476,20 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
               ht = adv ? hb : ht;
               hb = adv ? q2 : hb;
               q2 = adv ? q3 : q2;
-              q3 = adv ? q4 : q3;
-              q4 = adv ? q5 : q4;
+              if (kDeep) {
+                q3 = adv ? q4 : q3;
+                q4 = adv ? q5 : q4;
+              }
               dh = hb - ht;
             }
           };
-          if (aligned) walk(std::true_type{});
-          else walk(std::false_type{});
+          if (aligned) {
+            if (deep) walk(std::true_type{}, std::true_type{});
+            else walk(std::true_type{}, std::false_type{});
+          } else {
+            if (deep) walk(std::false_type{}, std::true_type{});
+            else walk(std::false_type{}, std::false_type{});
+          }
           PROF_ADD(9, PROF_NOW - it_t1)
           continue;
         }

@@ -88,6 +88,29 @@ def test_every_box_meets_every_tile(cuda_device):
     _check_image(im, np.float64)
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_shape_sweep(cuda_device, seed):
+    """Seeded sweep over odd canvas sizes, instance counts and class counts: tile widths of
+    1 .. 40 column blocks, aligned and unaligned rows, partial last tiles in both directions,
+    boxes from 1 px to the whole window."""
+    rng = np.random.default_rng(1000 + seed)
+    H = int(rng.integers(17, 260))
+    W = int(rng.integers(16, 420))
+    R = int(rng.choice([1, 2, 3, 7, 16, 33, 64, 100]))
+    n = int(rng.integers(0, R + 1))
+    classes = int(rng.choice([2, 3, 81]))
+    im = synth.make_image(rng, (H, W), n, num_classes=classes, max_instances=R,
+                          min_box=1, max_box_frac=float(rng.choice([0.1, 0.5, 1.0])))
+    dtype = np.float64 if seed % 2 else np.float32
+    if n == 0:      # upstream returns np.empty((H, W, 0)) (float64), not a bool array
+        got = api_utils.unmold_detections(*item_of(im, dtype))
+        ref = oracle_unmold(im, dtype)
+        assert got[3].shape == ref[3].shape == (H, W, 0) and got[3].dtype == ref[3].dtype
+        assert got[0].shape == (0, 4)
+        return
+    _check_image(im, dtype)
+
+
 def test_small_boxes_downscale(cuda_device):
     # boxes smaller than the 28x28 tile (no anti-aliasing in the reference)
     rng = np.random.default_rng(8)
