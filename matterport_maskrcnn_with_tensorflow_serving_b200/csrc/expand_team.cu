@@ -21,7 +21,7 @@
 //               | others   : cull the boxes of the next tile into the team's entry list
 //            B2 | all      : zero the buffer  (this IS the canvas zero fill)
 //            B3 | all      : items = (entry, 32-column block), dealt round robin to the warps:
-//               |            fetch up to six tile rows, interpolate them horizontally with two
+//               |            fetch four (or six) tile rows, interpolate them horizontally with two
 //               |            warp shuffles each, then walk the canvas rows: one FFMA, one
 //               |            compare, one st.shared.u8 per row, the (ht, hb) pair advancing
 //               |            through a register queue by predicate -- straight-line code
@@ -426,10 +426,11 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
         asm volatile("" : "+r"(step), "+r"(one));   // keep them in registers (ptxas re-reads the constant bank / re-materialises per row otherwise)
         if (Dy > step && remy + (cnt - 1) * step < 5 * Dy) {
           // ---- the common case: a box tall enough that the tile meets at most 6 of its source
-          // rows (jcur .. jcur+5).  Straight-line, branch-free: all six rows are fetched and
-          // interpolated horizontally up front; the canvas rows then walk a register queue
-          // (ht, hb, q2..q5) that shifts by predicate when the source row advances.  Rows past
-          // the box (i >= cnt) are predicated off.
+          // rows (jcur .. jcur+5).  Straight-line, branch-free: the rows are fetched and
+          // interpolated horizontally up front (four of them, six when more than two advances
+          // are possible inside the tile); the canvas rows then walk a register queue
+          // (ht, hb, q2, q3 [, q4, q5]) that shifts by predicate when the source row advances.
+          // Rows past the box (i >= cnt) are predicated off.
           // rows jcur .. jcur+5 of the tile in lane-column layout; row k is real when
           // 0 <= jcur + k < mh (only k = 0 can be the zero row above the tile: jcur >= -1)
           const int lim = lanecol ? mh - jcur : 0;   // row k is inside the tile iff k < lim
