@@ -172,3 +172,28 @@ def test_dropin_shims_resolve_the_reference_imports():
             "print('ok')") % os.path.join(ROOT, "dropin")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_overlay_host_logic_matches_oracle():
+    """visualize.random_colors / blend_table: the colour values and the float64 evaluation
+    order `alpha * color[c] * 255` the reference's apply_mask uses (no GPU needed)."""
+    import random
+
+    from matterport_maskrcnn_with_tensorflow_serving_b200 import visualize
+
+    assert visualize.random_colors(11, rng=random.Random(2)) == oracle.random_colors(11, rng=random.Random(2))
+    assert visualize.random_colors(5, bright=False, rng=random.Random(0)) == \
+        oracle.random_colors(5, bright=False, rng=random.Random(0))
+    cols = oracle.random_colors(7, rng=random.Random(9))
+    tab = visualize.blend_table(cols, 0.3, 10)
+    assert tab.shape == (10, 3) and tab.dtype == np.float64
+    for i, col in enumerate(cols):
+        for c in range(3):
+            assert tab[i, c] == 0.3 * col[c] * 255
+    assert not tab[7:].any()
+    # without CUDA the product raises instead of falling back
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(N.MrxError):
+            visualize.apply_masks(np.zeros((4, 4, 3), np.uint8), np.zeros((1, 4), np.int32),
+                                  np.zeros((4, 4, 1), bool), cols)
