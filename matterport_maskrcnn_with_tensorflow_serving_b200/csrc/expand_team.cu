@@ -331,13 +331,14 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     // canvas zero fill (fixed trip count: predicated stores, no loop bookkeeping)
     if (!(p.flags & 0x200)) {
       uint4 *o4 = reinterpret_cast<uint4 *>(s_buf);
-      const int n16 = (kk * pitch) >> 4;
-      constexpr int kMaxZero = (232448 / kTeams / 16 + kTeamThreads - 1) / kTeamThreads;
+      const int rem = ((kk * pitch) >> 4) - tt;   // 16-byte words from this thread's first one on
+      // the largest tile buffer a team can get (232 448 B of shared memory per CTA)
+      constexpr int kMaxBuf = (232448 - kTeams * (kCand * static_cast<int>(sizeof(TEntry)) +
+                                                  2 * static_cast<int>(sizeof(TJob)))) / kTeams;
+      constexpr int kMaxZero = (kMaxBuf / 16 + kTeamThreads - 1) / kTeamThreads;
 #pragma unroll
-      for (int k = 0; k < kMaxZero; ++k) {
-        const int i = tt + k * kTeamThreads;
-        if (i < n16) o4[i] = make_uint4(0u, 0u, 0u, 0u);
-      }
+      for (int k = 0; k < kMaxZero; ++k)
+        if (k * kTeamThreads < rem) o4[tt + k * kTeamThreads] = make_uint4(0u, 0u, 0u, 0u);
     }
     int cbase = 0;
     PROF_MARK(1)
@@ -614,7 +615,10 @@ static int launch_team_cfg(const ExpandParams &prm, int sms, int max_optin, int 
                        static_cast<size_t>(prm.B + 1) * sizeof(int) + kStatic;
   MRX_CHECK_SUPPORTED(fixed + static_cast<size_t>(kTeams) * 2048 <= static_cast<size_t>(max_optin),
                       "mrx_mask_expand: batch of %d images does not fit the scheduler table", prm.B);
-  const int avail = static_cast<int>((static_cast<size_t>(max_optin) - fixed) / kTeams) & ~127;
+  // (the kernel's zero fill is unrolled for tile buffers of up to this size)
+  constexpr int kMaxBuf = (232448 - kTeams * (kCand * static_cast<int>(sizeof(TEntry)) +
+                                              2 * static_cast<int>(sizeof(TJob)))) / kTeams;
+  const int avail = min(static_cast<int>((static_cast<size_t>(max_optin) - fixed) / kTeams), kMaxBuf) & ~127;
   // a tile row must hold 16 pixels of R instances (aligned shapes) / one pixel + alignment shift
   const int need = (max(16 * prm.R, prm.R + 48) * kTileRows + 127) & ~127;
   if (need > avail) return MRX_E_UNSUPPORTED;   // caller falls back to the generic kernel
