@@ -66,6 +66,11 @@ def _squeeze_inputs(detections, mrcnn_mask):
         detections = detections.astype(np.float64)
     if mrcnn_mask.dtype not in (np.float32, np.float64):
         mrcnn_mask = mrcnn_mask.astype(np.float64)
+    # zero-copy views of a received message (wire.py) are read-only; torch wants writable memory
+    if not mrcnn_mask.flags.writeable:
+        mrcnn_mask = mrcnn_mask.copy()
+    if not detections.flags.writeable:
+        detections = detections.copy()
     return np.ascontiguousarray(detections), np.ascontiguousarray(mrcnn_mask)
 
 

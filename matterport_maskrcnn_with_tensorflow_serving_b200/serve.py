@@ -6,7 +6,9 @@
 
 The TensorFlow-Serving RPC itself (serve.py:26-80) is out of scope and is injected:
 `set_predict_fn(fn)` installs `fn(molded_image_f32, image_meta_f32, anchors_f32) ->
-(mrcnn_detection, mrcnn_mask)`; without one `grpc_inference` raises.  Rendering the PNG
+(mrcnn_detection, mrcnn_mask)` -- float lists / arrays as `float_val` gives them, or the
+`TensorProto` messages themselves (or their bytes), which are then decoded from the wire format
+without a Python float per element (`wire.py`); without one `grpc_inference` raises.  Rendering the PNG
 (`visualize.display_instances`, serve.py:160-169) is also out of scope, so `do_inference`
 returns the unmolded tuple instead of a file path.
 """
@@ -16,6 +18,7 @@ import numpy as np
 
 from . import api_utils
 from . import configs as cf
+from . import wire
 from .engine import Molder
 
 _predict_fn = None
@@ -63,6 +66,10 @@ def preprocess_input(img, img_size=640, molded_dtype=np.float64):
     return molded_image, image_meta, anchors, window
 
 
+def _is_tensor_proto(x):
+    return isinstance(x, (bytes, bytearray, memoryview)) or hasattr(x, "SerializeToString")
+
+
 def grpc_inference(img):
     """serve.py:110-138 with the RPC injected (see module docstring)."""
     if _predict_fn is None:
@@ -71,6 +78,12 @@ def grpc_inference(img):
     mrcnn_detection, mrcnn_mask = _predict_fn(
         molded_image.astype(np.float32), image_meta.astype(np.float32),
         anchors.astype(np.float32))
+    if _is_tensor_proto(mrcnn_detection) and _is_tensor_proto(mrcnn_mask):
+        # result.outputs[...] handed over as TensorProto messages (or their bytes): take the
+        # values from the wire instead of through per-element Python floats (wire.py)
+        mrcnn_detection, mrcnn_mask = wire.decode_predict_outputs(
+            mrcnn_detection, mrcnn_mask, cf.OUT_DETECTION_SHAPE, cf.OUT_MASK_SHAPE)
+        return mrcnn_detection, mrcnn_mask, molded_image, window
     # serve.py:131-136: float_val lists become float64 arrays with a leading -1 dim
     mrcnn_detection = np.array(mrcnn_detection).reshape((-1, *cf.OUT_DETECTION_SHAPE))
     mrcnn_mask = np.array(mrcnn_mask).reshape((-1, *cf.OUT_MASK_SHAPE))

@@ -91,3 +91,41 @@ def test_preprocess_input_matches_reference_flow(cuda_device, img_size):
     assert molded.dtype == ref_molded.dtype and np.array_equal(molded, ref_molded)
     assert np.array_equal(meta, ref_meta)
     assert np.array_equal(anchors.view(np.uint32), ref_anchors.view(np.uint32))
+
+
+def test_do_inference_flow_lists_and_wire_bytes(cuda_device):
+    """serve.py:141-154 end to end around an injected TF-Serving call: the model outputs arrive
+    once as float lists (what `float_val` yields, serve.py:131-136) and once as serialized
+    TensorProto messages (wire.py); both must equal the oracle's unmold of the same outputs."""
+    from matterport_maskrcnn_with_tensorflow_serving_b200 import configs as cf
+    from matterport_maskrcnn_with_tensorflow_serving_b200 import wire
+
+    rng = np.random.default_rng(9)
+    img = synth.synth_rgb_image(rng, 480, 640)
+    molded, meta, anchors, window = serve.preprocess_input(img, cf.IMAGE_SIZE)
+    im = synth.make_image(rng, img.shape[:2], 17, num_classes=cf.OUT_MASK_SHAPE[-1],
+                          max_instances=cf.OUT_DETECTION_SHAPE[0], mold=(molded.shape, window))
+    det32, msk32 = im.detections, im.mrcnn_mask
+    ref = oracle.unmold_detections(det32.astype(np.float64), msk32.astype(np.float64),
+                                   img.shape, molded.shape, window)
+    seen = {}
+
+    def predict_lists(molded_f32, meta_f32, anchors_f32):
+        seen["dtypes"] = (molded_f32.dtype, meta_f32.dtype, anchors_f32.dtype)
+        return det32.reshape(-1).tolist(), msk32.reshape(-1).tolist()
+
+    def predict_wire(molded_f32, meta_f32, anchors_f32):
+        return (wire.ndarray_to_tensor_proto_bytes(det32[None]),
+                wire.ndarray_to_tensor_proto_bytes(msk32[None]))
+
+    try:
+        for fn in (predict_lists, predict_wire):
+            serve.set_predict_fn(fn)
+            b, c, s, m = serve.do_inference(img)
+            assert np.array_equal(b, ref[0]) and np.array_equal(c, ref[1])
+            assert np.array_equal(s, ref[2]) and s.dtype == ref[2].dtype
+            assert m.shape == ref[3].shape and m.dtype == np.bool_
+            assert (m != ref[3]).sum() == 0      # seeded data: no pixel inside the 1e-6 band
+        assert seen["dtypes"] == (np.float32, np.float32, np.float32)    # serve.py:117-119
+    finally:
+        serve.set_predict_fn(None)
