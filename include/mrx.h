@@ -12,6 +12,7 @@
  *   mrx_cv2_resize_u8c3    <- cv2.resize(img, (S, S))                     serve.py:88-89
  *   mrx_mold_image         <- resize_image + mold_image                   serve.py:91-98
  *   mrx_composite_masks    <- visualize.display_instances (mask overlay)  serve.py:160-169
+ *   mrx_pack_masks         (extension: bit-packed transport of the masks of serve.py:147)
  *
  * Conventions
  *   - every pointer named d_* is DEVICE memory owned by the caller (the Python
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define MRX_ABI_VERSION 3
+#define MRX_ABI_VERSION 4
 
 #define MRX_OK              0
 #define MRX_E_INVALID      -1   /* bad argument (null pointer, size out of range) */
@@ -163,6 +164,18 @@ int mrx_composite_masks(const unsigned char *d_canvas, const long long *d_canvas
                         const double *d_blend, double one_minus_alpha,
                         unsigned char *d_out, int B, int R, long long max_pixels,
                         void *stream);
+
+/* ---------------------------------------------------------------- packed masks (8f) */
+/* EXTENSION (not the reference layout): bit-packed copy of the canvases for transport.
+ * For image b:  d_packed + d_packed_off[b]  holds  uint8 [N_b, H_b, ceil(W_b/8)]  with
+ *     packed[n, y, :] = np.packbits(masks[y, :, n])          (most significant bit first)
+ * so that np.unpackbits(packed, axis=-1, count=W).transpose(1, 2, 0) is the bool [H,W,N] array
+ * unmold_detections returns.  Slot b must hold R * H_b * ceil(W_b/8) bytes; d_packed_off int64.
+ * max_h / max_w: largest H_b / W_b of the batch (grid sizing). */
+int mrx_pack_masks(const unsigned char *d_canvas, const long long *d_canvas_off,
+                   const int *d_counts, const int *d_geom, unsigned char *d_packed,
+                   const long long *d_packed_off, int B, int R, int max_h, int max_w,
+                   void *stream);
 
 #ifdef __cplusplus
 }

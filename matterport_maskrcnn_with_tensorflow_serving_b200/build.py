@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmrx.so")
 STAMP_PATH = os.path.join(LIB_DIR, "libmrx.stamp")
 
-SOURCES = ["capi.cu", "anchors.cu", "unmold.cu", "expand_team.cu", "expand_ws4.cu", "mold.cu", "composite.cu"]
+SOURCES = ["capi.cu", "anchors.cu", "unmold.cu", "expand_team.cu", "expand_ws4.cu", "mold.cu", "composite.cu", "pack.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "expand.cuh"),
            os.path.join(os.path.dirname(PKG_DIR), "include", "mrx.h")]
 

@@ -185,6 +185,33 @@ class UnmoldEngine:
         o = int(self._offsets[b])
         return self.d_canvas[o:o + H * W * n_kept].view(H, W, n_kept)
 
+    def pack_masks(self, stream=None):
+        """EXTENSION (not the reference layout): bit-pack the canvases of the planned batch on the
+        device.  Returns (d_packed uint8 tensor, offsets int64 array [n+1]); image b occupies
+        d_packed[off[b]:off[b+1]] as [R, H_b, ceil(W_b/8)], the first N_b planes are valid:
+        packed[n, y] == np.packbits(masks[y, :, n])."""
+        torch = _torch()
+        n = self._n_images
+        if n == 0:
+            raise RuntimeError("plan() first")
+        g = self._geom_host
+        wb = (g[:, 1].astype(np.int64) + 7) // 8
+        sizes = g[:, 0].astype(np.int64) * wb * self.R
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(sizes, out=off[1:])
+        total = int(off[-1])
+        if getattr(self, "d_packed", None) is None or self.d_packed.numel() < total:
+            self.d_packed = torch.empty((total,), dtype=torch.uint8, device=self.device)
+        if getattr(self, "_packed_off_host", None) is None or \
+                not np.array_equal(self._packed_off_host, off):
+            self.d_packed_off = torch.from_numpy(off[:n].copy()).to(self.device)
+            self._packed_off_host = off
+        N.check(self.lib.mrx_pack_masks(
+            _ptr(self.d_canvas), _ptr(self.d_canvas_off), _ptr(self.d_counts), _ptr(self.d_geom),
+            _ptr(self.d_packed), _ptr(self.d_packed_off), n, self.R,
+            int(g[:, 0].max()), int(g[:, 1].max()), N.stream_ptr(stream)), "mrx_pack_masks")
+        return self.d_packed, off
+
     def fetch_meta(self):
         """Copy counts/status/boxes/class_ids/scores of the planned batch to the host
         (synchronises the current stream). Raises like numpy would on bad inputs."""
