@@ -54,12 +54,20 @@ pack_masks_kernel(const unsigned char *__restrict__ canvas, const long long *__r
   unsigned char *dst = packed + packed_off[b] + (static_cast<long long>(y) * wb + bx);
   const long long plane = static_cast<long long>(H) * wb;
   const unsigned char *mine = smem + static_cast<size_t>(px) * N;
+  // one 4-byte store per (warp, instance) when the warp's four bytes exist and every plane's
+  // copy of them is 4-byte aligned; byte stores otherwise (row ends, odd row pitches)
+  const bool word_ok = nb == 4 && ((reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(plane)) & 3u) == 0u;
   for (int n = 0; n < N; ++n) {
     const unsigned bit = valid ? (mine[n] != 0) : 0u;
     const unsigned bal = __ballot_sync(0xffffffffu, bit);
     // ballot bit l = pixel l; packbits puts pixel 0 in the most significant bit of byte 0
     const unsigned rev = __brev(bal);                // bit 31 = pixel 0
-    if (lane < nb) dst[n * plane + lane] = static_cast<unsigned char>(rev >> (24 - 8 * lane));
+    if (word_ok) {
+      // memory order byte0..byte3 = rev bits 31..24, 23..16, 15..8, 7..0
+      if (lane == 0) *reinterpret_cast<unsigned *>(dst + n * plane) = __byte_perm(rev, 0u, 0x0123);
+    } else if (lane < nb) {
+      dst[n * plane + lane] = static_cast<unsigned char>(rev >> (24 - 8 * lane));
+    }
   }
 }
 
