@@ -63,8 +63,25 @@ def resize_case():
     np.savez_compressed(os.path.join(HERE, "resize.npz"), **out)
 
 
+def composite_case():
+    """Overlay of display_instances on the unmold_small masks."""
+    import random
+
+    g = np.load(os.path.join(HERE, "unmold_small.npz"))
+    shape = tuple(int(v) for v in g["masks_shape"])
+    masks = np.unpackbits(g["masks_packed"], count=int(np.prod(shape))).reshape(shape).astype(bool)
+    rng = np.random.default_rng(7)
+    image = synth.synth_rgb_image(rng, shape[0], shape[1])
+    colors = oracle.random_colors(shape[2], rng=random.Random(11))
+    out = oracle.composite_instances(image, g["boxes"], masks, colors, alpha=0.5)
+    np.savez_compressed(os.path.join(HERE, "composite_small.npz"), image=image,
+                        colors=np.array(colors, dtype=np.float64), overlay=out)
+    print("composite_small", out.shape, "sha", hashlib.sha256(out.tobytes()).hexdigest()[:12])
+
+
 if __name__ == "__main__":
     unmold_case("unmold_small", 101, (96, 128), 12, 5, 16, zero_area_rows=(3,))
     unmold_case("unmold_coco_shape", 102, (120, 200), 9, 4, 12)
     anchors_case()
     resize_case()
+    composite_case()

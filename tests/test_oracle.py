@@ -201,3 +201,15 @@ def test_composite_known_answers():
     assert out[0, 1].tolist() == [100, 100, 100]
     assert len(oracle.random_colors(7)) == 7 and oracle.random_colors(4)[0] in [
         (1.0, 0.0, 0.0), (0.5, 1.0, 0.0), (0.0, 1.0, 1.0), (0.5, 0.0, 1.0)]
+
+
+def test_composite_golden():
+    """The committed overlay of the unmold_small masks (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLD, "unmold_small.npz"))
+    c = np.load(os.path.join(GOLD, "composite_small.npz"))
+    shape = tuple(int(v) for v in g["masks_shape"])
+    masks = np.unpackbits(g["masks_packed"], count=int(np.prod(shape))).reshape(shape).astype(bool)
+    colors = [tuple(row) for row in c["colors"]]
+    out = oracle.composite_instances(c["image"], g["boxes"], masks, colors, alpha=0.5)
+    assert np.array_equal(out, c["overlay"])
+    assert (out != c["image"]).any()
