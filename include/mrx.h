@@ -9,10 +9,13 @@
  *   mrx_unmold_prologue    <- api_utils.unmold_detections(...) steps 1-6  serve.py:147-154
  *   mrx_gather_tiles       <- mrcnn_mask[arange(N),:,:,class_ids]         (same call)
  *   mrx_mask_expand        <- per-instance unmold_mask + np.stack(axis=-1)(same call)
- *   mrx_cv2_resize_u8c3    <- cv2.resize(img, (S, S))                     serve.py:88-89
- *   mrx_mold_image         <- resize_image + mold_image                   serve.py:91-98
+ *   mrx_mask_expand_values    (parity instrumentation of the kernel above)
+ *   mrx_cv2_resize_u8c3[_batch] <- cv2.resize(img, (S, S))                serve.py:88-89
+ *   mrx_mold_image[_batch] <- resize_image + mold_image                   serve.py:91-98
  *   mrx_composite_masks    <- visualize.display_instances (mask overlay)  serve.py:160-169
  *   mrx_pack_masks         (extension: bit-packed transport of the masks of serve.py:147)
+ *   mrx_mask_expand_packed (extension: the expand step writing that packed layout directly)
+ *   mrx_peer_*             (multi-GPU: the final gather of the masks to rank 0)
  *
  * Conventions
  *   - every pointer named d_* is DEVICE memory owned by the caller (the Python
@@ -33,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MRX_ABI_VERSION 4
+#define MRX_ABI_VERSION 5
 
 #define MRX_OK              0
 #define MRX_E_INVALID      -1   /* bad argument (null pointer, size out of range) */
@@ -91,12 +94,13 @@ int mrx_anchors(float *d_out, int img_h, int img_w,
  *     (64*mw) div/mod 2*bw); consumed by mrx_mask_expand
  *   d_counts [B] int32 (N per image)    d_status [B] int32 (MRX_ST_* bits)
  * C = number of classes in mrcnn_mask's last axis (for the class-range check).
- * Also resets *d_job_counter (uint32) used by mrx_mask_expand's scheduler. */
+ * d_sched (may be NULL): the scheduler words of the expand kernels (MRX_SCHED_WORDS x uint32),
+ * zeroed here as well. */
 int mrx_unmold_prologue(const void *d_detections, int det_dtype, int B, int R, int C,
                         int mw, const int *d_geom,
                         int *d_boxes, int *d_class_ids, void *d_scores,
                         int *d_src_index, int *d_box_aux, int *d_counts, int *d_status,
-                        unsigned int *d_job_counter, void *stream);
+                        unsigned int *d_sched, void *stream);
 
 /* masks = mrcnn_mask[src_index, :, :, class_id] packed to float32 tiles.
  *   d_mrcnn_mask [B,R,mh,mw,C] mask_dtype  ->  d_tiles [B,R,mh,mw] float32      */
@@ -104,6 +108,11 @@ int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype,
                      int B, int R, int mh, int mw, int C,
                      const int *d_class_ids, const int *d_src_index,
                      const int *d_counts, float *d_tiles, void *stream);
+
+/* Scheduler scratch of the expand kernels: MRX_SCHED_WORDS x uint32 of device memory that the
+ * caller zeroes ONCE after allocating it; every launch hands out its work through it and leaves
+ * it zeroed (no memset between launches).  One scratch per stream of launches. */
+#define MRX_SCHED_WORDS 4
 
 /* The hot kernel.  For every image b writes the bool canvas [H_b, W_b, N_b]
  * (N innermost, 1 byte per element, values 0/1) at d_canvas + d_canvas_off[b]:
@@ -121,20 +130,33 @@ int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_box_a
                     const int *d_counts, const int *d_geom, const long long *d_canvas_off,
                     unsigned char *d_canvas, int B, int R, int mh, int mw,
                     int chunk_bytes, int ctas_per_sm,
-                    unsigned int *d_job_counter, void *stream);
+                    unsigned int *d_sched, void *stream);
 
-/* Pre-threshold resized values of one instance (test hook for the stated fp32
- * tolerance): d_out [bh, bw] float32 for box (y1,x1,y2,x2); same exact integer source
- * coordinates and fp32 weights as mrx_mask_expand (which applies the two lerps in the
- * other order: horizontal first; both stay within the 1e-6 contract). */
-int mrx_resize_tile_f32(const float *d_tile, int mh, int mw, int bh, int bw,
-                        float *d_out, void *stream);
+/* Parity instrumentation: the SAME kernel template as mrx_mask_expand (same culling, source
+ * coordinates, interpolation and row walk -- a second instantiation of it), which in addition
+ * stores every pre-threshold sample it evaluates: d_values is float32, indexed exactly like
+ * d_canvas (element d_canvas_off[b] + (y*W_b + x)*N_b + n); only elements inside box n are
+ * written.  The canvas is written as usual.  Tests compare these values with the float64
+ * oracle (|diff| <= 1e-6).  Shapes the team kernel does not take (R > 200, mask tiles wider
+ * than 30 columns) return MRX_E_UNSUPPORTED. */
+int mrx_mask_expand_values(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
+                           const int *d_counts, const int *d_geom, const long long *d_canvas_off,
+                           unsigned char *d_canvas, float *d_values, int B, int R, int mh, int mw,
+                           unsigned int *d_sched, void *stream);
 
 /* ---------------------------------------------------------------- mold (a6) */
 /* cv2.resize(src, (dst_w, dst_h)) for uint8 HxWx3, default INTER_LINEAR
  * (OpenCV's 11-bit fixed-point path, incl. its exact-2x INTER_AREA shortcut). */
 int mrx_cv2_resize_u8c3(const unsigned char *d_src, int src_h, int src_w,
                         unsigned char *d_dst, int dst_h, int dst_w, void *stream);
+
+/* The same for a batch in ONE launch (the reference resizes every request image to
+ * (IMAGE_SIZE, IMAGE_SIZE), serve.py:88-89, 114): sources of any sizes, image b at
+ * d_src + d_src_off[b] (int64 byte offsets) with (h, w) = d_src_hw[2b], d_src_hw[2b+1];
+ * destinations densely packed [B, dst_h, dst_w, 3]. */
+int mrx_cv2_resize_u8c3_batch(const unsigned char *d_src, const long long *d_src_off,
+                              const int *d_src_hw, unsigned char *d_dst, int B,
+                              int dst_h, int dst_w, void *stream);
 
 /* resize_image(mode square/pad64/none geometry precomputed by the host) fused
  * with mold_image: scale src (uint8 HxWx3) to new_h x new_w with the zero-border
@@ -147,6 +169,13 @@ int mrx_mold_image(const unsigned char *d_src, int src_h, int src_w,
                    int new_h, int new_w, int top, int left, int out_h, int out_w,
                    const double *mean_pixel /* host, 3 */, int out_dtype,
                    void *d_out, unsigned char *d_molded_u8, void *stream);
+
+/* The same for B equally sized images in ONE launch: d_src [B,src_h,src_w,3] ->
+ * d_out [B,out_h,out_w,3] (and d_molded_u8 likewise). */
+int mrx_mold_image_batch(const unsigned char *d_src, int B, int src_h, int src_w,
+                         int new_h, int new_w, int top, int left, int out_h, int out_w,
+                         const double *mean_pixel /* host, 3 */, int out_dtype,
+                         void *d_out, unsigned char *d_molded_u8, void *stream);
 
 /* ---------------------------------------------------------------- compositing (8f) */
 /* Mask part of visualize.display_instances(img, boxes, masks, ...) (serve.py:160-169), on
@@ -176,6 +205,37 @@ int mrx_pack_masks(const unsigned char *d_canvas, const long long *d_canvas_off,
                    const int *d_counts, const int *d_geom, unsigned char *d_packed,
                    const long long *d_packed_off, int B, int R, int max_h, int max_w,
                    void *stream);
+
+/* EXTENSION: the expand step with bit-packed output, without ever writing the byte canvas
+ * (expand_bits.cu).  Same inputs as mrx_mask_expand (tiles, boxes, counts, geometry as left by
+ * mrx_unmold_prologue / mrx_gather_tiles); output layout exactly that of mrx_pack_masks:
+ * image b at d_packed + d_packed_off[b] as uint8 [N_b, H_b, ceil(W_b/8)] (slot capacity
+ * R * H_b * ceil(W_b/8)); planes n >= N_b are not written.  The samples are computed with the
+ * same arithmetic as mrx_mask_expand, so  packed == np.packbits(canvas)  bit for bit.
+ * d_packed may be memory of ANOTHER GPU mapped with mrx_peer_open (fused compute + gather).
+ * max_w: widest W_b of the batch.  Mask tiles wider than 30 columns: MRX_E_UNSUPPORTED
+ * (use mrx_mask_expand + mrx_pack_masks). */
+int mrx_mask_expand_packed(const float *d_tiles, const int *d_boxes, const int *d_counts,
+                           const int *d_geom, const long long *d_packed_off,
+                           unsigned char *d_packed, int B, int R, int mh, int mw, int max_w,
+                           unsigned int *d_sched, void *stream);
+
+/* ---------------------------------------------------------------- multi-GPU gather (8e) */
+/* Peer-memory plumbing for the final gather of the canvases to rank 0 (one process per GPU).
+ * Rank 0: mrx_peer_alloc a receive buffer + mrx_peer_export its 64-byte handle; other ranks:
+ * mrx_peer_open the handle and pass the mapped address as the OUTPUT pointer of
+ * mrx_mask_expand / mrx_mask_expand_packed -- the kernels store over NVLink straight into
+ * rank 0's HBM.  mrx_peer_signal(flag, v, stream): after everything queued on `stream` so far,
+ * store v to *flag (system scope, release).  mrx_peer_wait(flags, n, v, stream): `stream`
+ * proceeds once flags[0..n) are all >= v (acquire).  Flags live in peer-allocated memory. */
+#define MRX_PEER_HANDLE_BYTES 64
+int mrx_peer_alloc(unsigned long long bytes, void **d_ptr);
+int mrx_peer_free(void *d_ptr);
+int mrx_peer_export(void *d_ptr, unsigned char *handle64);
+int mrx_peer_open(const unsigned char *handle64, void **d_ptr);
+int mrx_peer_close(void *d_ptr);
+int mrx_peer_signal(unsigned int *d_flag, unsigned int value, void *stream);
+int mrx_peer_wait(const unsigned int *d_flags, int n_flags, unsigned int value, void *stream);
 
 #ifdef __cplusplus
 }

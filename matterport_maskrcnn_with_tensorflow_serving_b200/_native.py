@@ -11,7 +11,9 @@ import os
 import re
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libmrx.so")
+# MRX_LIB=<file name under lib/> selects another build of the library (development only:
+# e.g. libmrx_dev.so built with MRX_NVCC_FLAGS=-DMRX_DEV); the default is the shipped one
+LIB_PATH = os.path.join(_PKG_DIR, "lib", os.environ.get("MRX_LIB", "libmrx.so"))
 HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "mrx.h")
 
 MRX_OK = 0
@@ -21,7 +23,9 @@ MRX_ST_CLASS_RANGE = 1
 MRX_ST_BOX_RANGE = 2
 MRX_GEOM_INTS = 8
 MRX_MAX_BATCH = 4096
-ABI_VERSION = 4
+ABI_VERSION = 5
+MRX_SCHED_WORDS = 4
+MRX_PEER_HANDLE_BYTES = 64
 
 
 class MrxError(RuntimeError):
@@ -43,9 +47,21 @@ SIGNATURES = {
     "mrx_gather_tiles": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mrx_mask_expand": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp,
                              _vp]),
-    "mrx_resize_tile_f32": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "mrx_mask_expand_values": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp,
+                                    _vp]),
+    "mrx_mask_expand_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "mrx_peer_alloc": (_i, [C.c_ulonglong, C.POINTER(C.c_void_p)]),
+    "mrx_peer_free": (_i, [_vp]),
+    "mrx_peer_export": (_i, [_vp, C.c_char_p]),
+    "mrx_peer_open": (_i, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mrx_peer_close": (_i, [_vp]),
+    "mrx_peer_signal": (_i, [_vp, C.c_uint, _vp]),
+    "mrx_peer_wait": (_i, [_vp, _i, C.c_uint, _vp]),
     "mrx_cv2_resize_u8c3": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "mrx_mold_image": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _dp, _i, _vp, _vp, _vp]),
+    "mrx_cv2_resize_u8c3_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "mrx_mold_image_batch": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, _i, _vp, _vp,
+                                  _vp]),
     "mrx_composite_masks": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _i, _i,
                                  C.c_longlong, _vp]),
     "mrx_pack_masks": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -69,11 +85,19 @@ def load(build_if_missing=True):
         return _lib
     import torch  # noqa: F401  (loads libcudart.so.12 before libmrx.so asks for it)
 
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise MrxError(f"{LIB_PATH} is missing; run __graft_entry__.build()")
+    default_lib = os.path.basename(LIB_PATH) == "libmrx.so"
+    if build_if_missing and default_lib:
+        # cheap when nothing changed (a digest of the sources against lib/libmrx.stamp); a stale
+        # library whose ABI number happens to match is rebuilt instead of silently used.  Without
+        # nvcc (a deployment box) the prebuilt library is used as it is.
         from . import build as _build
-        _build.build()
+        try:
+            _build.build()
+        except RuntimeError:
+            if not os.path.exists(LIB_PATH):
+                raise
+    if not os.path.exists(LIB_PATH):
+        raise MrxError(f"{LIB_PATH} is missing; run __graft_entry__.build()")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError if the symbol is not exported

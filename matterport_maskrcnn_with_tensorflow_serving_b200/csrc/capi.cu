@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mrx {
@@ -13,6 +15,36 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
   va_end(ap);
+}
+
+// ---- per-device launch constants, queried once (not on every launch)
+static std::mutex g_dev_mutex;
+static DevInfo g_dev_info[kMaxDevices];
+static bool g_dev_known[kMaxDevices];
+
+int current_device_info(DevInfo *out) {
+  int dev = 0;
+  MRX_CUDA(cudaGetDevice(&dev));
+  MRX_CHECK_SUPPORTED(dev >= 0 && dev < kMaxDevices, "device ordinal %d not supported", dev);
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (!g_dev_known[dev]) {
+    DevInfo d;
+    d.device = dev;
+    MRX_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    MRX_CUDA(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    g_dev_info[dev] = d;
+    g_dev_known[dev] = true;
+  }
+  *out = g_dev_info[dev];
+  return MRX_OK;
+}
+
+int ensure_dynamic_smem(const void *func, SmemCache *cache, int device, int bytes) {
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (cache->set[device] >= bytes) return MRX_OK;
+  MRX_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  cache->set[device] = bytes;
+  return MRX_OK;
 }
 
 }  // namespace mrx

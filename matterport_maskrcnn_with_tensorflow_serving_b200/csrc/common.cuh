@@ -47,6 +47,22 @@ void set_error(const char *fmt, ...);
     }                                                                          \
   } while (0)
 
+// ---------------------------------------------------------------- host-side launch constants
+constexpr int kMaxDevices = 64;
+
+struct DevInfo {
+  int device, sms, max_smem_optin;
+};
+// SM count / opt-in shared memory of the current device, queried once per device.
+int current_device_info(DevInfo *out);
+
+// Remembers, per device, the dynamic shared-memory size a kernel has been opted into, so that
+// cudaFuncSetAttribute runs when the requirement grows, not on every launch.
+struct SmemCache {
+  int set[kMaxDevices];
+};
+int ensure_dynamic_smem(const void *func, SmemCache *cache, int device, int bytes);
+
 // ---------------------------------------------------------------- device: PTX wrappers
 #if defined(__CUDACC__)
 

@@ -1,11 +1,11 @@
-// expand_team.cu -- mask-expand kernel, generation 6 (the default): 2-D canvas tiles built by
-// TEAMS of warps.  Replaces the producer / consumer / store-warp roles of generations 3-5
-// (expand_ws4.cu; generation 5 was dropped) with one role per warp and three named barriers per tile.
+// expand_team.cu -- the mask-expand kernel (the hot kernel of the path): 2-D canvas tiles built by
+// TEAMS of warps, one role per warp and three named barriers per tile.
 //
 // Why: the store pattern alone (shared memory -> HBM bulk copies of k x 3200 B, no box work)
-// writes a B200 at ~7.4 TB/s (tools/store_ceiling.cu), but generation 4 reached 4.6 TB/s: its
-// producer warps -- one dependent instruction stream listing (box,row) entries and issuing a TMA
-// load per entry -- were the critical path.  Here a tile is kTileRows canvas rows high, so a
+// writes a B200 at ~7.4 TB/s (tools/store_ceiling.cu); a warp-specialised producer / consumer /
+// store-warp design over mbarrier rings (round 1, removed) reached 4.6 TB/s: its producer warps
+// -- one dependent instruction stream listing (box,row) entries and issuing a TMA load per
+// entry -- were the critical path.  Here a tile is kTileRows canvas rows high, so a
 // box meets a tile once (not once per row); the horizontal source coordinate of a 32-column
 // block is computed once and reused for every row; the bilinear sample is evaluated as
 //   v = ht + wy * (hb - ht),   ht / hb = horizontal interpolation of source rows j / j+1
@@ -34,15 +34,24 @@
 // aligned body goes out as a bulk copy and the <= 15 head / tail bytes as byte stores.
 // HBM sees every canvas byte written exactly once either way.
 //
-// Development switches (MRX_EXPAND_FLAGS): 0x100 no items, 0x200 no zero fill, 0x400 no store.
-// MRX_EXPAND_TEAMS=<teams>x<warps>x<rows> picks another compiled shape.  Build with
-// -DMRX_TEAM_PROFILE (MRX_NVCC_FLAGS) for per-phase cycle counts (tools/team_profile.py).
+// The same kernel template is instantiated a second time with kValues = true
+// (mrx_mask_expand_values): identical cull / hrow / walk code, plus a float store of every
+// pre-threshold sample -- the parity tests check the 1e-6 value contract on THIS code.
+//
+// Development builds only (-DMRX_DEV via MRX_NVCC_FLAGS; never in the shipped library):
+// MRX_EXPAND_FLAGS 0x100 no items, 0x200 no zero fill, 0x400 no store;
+// MRX_EXPAND_TEAMS=<teams>x<warps>x<rows> picks another compiled shape; -DMRX_TEAM_PROFILE adds
+// per-phase cycle counts (tools/team_profile.py).
 #include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
 
 #include "expand.cuh"
+
+#ifndef MRX_DEFAULT_WALK
+#define MRX_DEFAULT_WALK 1
+#endif
 
 namespace mrx {
 
@@ -134,11 +143,20 @@ __device__ long long g_team_prof[148 * 32 * 12];
 #define PROF_NOW 0
 #endif
 
+#ifdef MRX_DEV
+#define MRX_FLAG(p, bit) ((p).flags & (bit))
+#else
+#define MRX_FLAG(p, bit) 0
+#endif
+
 __device__ __forceinline__ void team_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int kTeams, int kTeamWarps, int kTileRows>
+// kValues: also store every pre-threshold sample as float (test instantiation, see the header).
+// kWalk: 0 = every lane advances the vertical source coordinate itself, row by row;
+//        1 = lane i computes row i's weight once per item, the rows read it with a shuffle.
+template <int kTeams, int kTeamWarps, int kTileRows, bool kValues, int kWalk>
 __global__ void __launch_bounds__(kTeams * kTeamWarps * 32, 1)
 mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
   static_assert(kTileRows <= 32 && kTeamWarps >= 3, "one store lane per tile row; cull + decode warps");
@@ -312,7 +330,22 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     s_ecount[tm][1] = 0;
   }
   team_bar(bar_id, kTeamThreads);
-  if (!s_job[0].valid) return;   // fewer tiles than teams: nothing for this team
+  // a team that is done says so; the last one of the grid leaves both scheduler words at zero
+  // for the next launch (no memset between launches)
+  auto retire = [&]() {
+    if (tt == 0) {
+      __threadfence();
+      const unsigned done = atomicAdd(p.job_counter + 1, 1u);
+      if (done == gridDim.x * kTeams - 1u) {
+        p.job_counter[0] = 0u;
+        p.job_counter[1] = 0u;
+      }
+    }
+  };
+  if (!s_job[0].valid) {   // fewer tiles than teams: nothing for this team
+    retire();
+    return;
+  }
   cull(s_job[0], 0, 0, wt, kTeamWarps);
 
   int slot = 0;      // s_job[slot] / s_ecount[tm][slot] belong to the tile being drawn
@@ -329,7 +362,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     const float *const tiles_b = jp->tiles_b;
     if (tt == 0) s_ecount[tm][slot ^ 1] = 0;   // the next tile's counter (idle since tile j-1)
     // canvas zero fill (fixed trip count: predicated stores, no loop bookkeeping)
-    if (!(p.flags & 0x200)) {
+    if (!MRX_FLAG(p, 0x200)) {
       uint4 *o4 = reinterpret_cast<uint4 *>(s_buf);
       const int rem = ((kk * pitch) >> 4) - tt;   // 16-byte words from this thread's first one on
       // the largest tile buffer a team can get (232 448 B of shared memory per CTA)
@@ -346,7 +379,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
       // ================= B3: buffer zeroed / entry list of this pass complete
       team_bar(bar_id, kTeamThreads);
       PROF_MARK(2)
-      const int E = (p.flags & 0x100) ? 0 : s_ecount[tm][slot];
+      const int E = MRX_FLAG(p, 0x100) ? 0 : s_ecount[tm][slot];
       // ---- items: (entry, 32-column block) pairs, item i = entry * nblk + block, dealt round
       // robin to the team's warps (at N = 100 a tile is one block wide and an item is an entry)
       const int nblk = (pw + 31) >> 5;
@@ -422,9 +455,17 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
         int jcur = eb.z, remy = eb.w;
         uint32_t addr = buf_addr + static_cast<uint32_t>(ra * pitch + (x - x0) * N + n);
         const int cnt = rb - ra;
+        // kValues: where the sample of (tile row ra, this lane's column, instance n) goes
+        [[maybe_unused]] float *vout = nullptr;
+        if (kValues)
+          vout = p.values + (g0 - p.canvas) + static_cast<size_t>(ra) * RW +
+                 static_cast<size_t>(x - x0) * N + n;
         int step = 2 * mh;
-        unsigned one = 1u;
-        asm volatile("" : "+r"(step), "+r"(one));   // keep them in registers (ptxas re-reads the constant bank / re-materialises per row otherwise)
+        // the byte every set sample stores: 1, derived from a value ptxas cannot fold (the sign
+        // bit of a pitch), or it re-materialises the constant (and a byte merge) in front of
+        // every one of the row stores
+        unsigned one = 1u ^ (static_cast<unsigned>(pitch) >> 31);
+        asm volatile("" : "+r"(step));   // one register, not a constant-bank read per row
         if (Dy > step && remy + (cnt - 1) * step < 5 * Dy) {
           // ---- the common case: a box tall enough that the tile meets at most 6 of its source
           // rows (jcur .. jcur+5).  Straight-line, branch-free: the rows are fetched and
@@ -456,6 +497,27 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
           PROF_ADD(8, it_t1 - it_t0)
           PROF_ADD(10, 1)
           PROF_ADD(11, cnt)
+          // kWalk == 1: the vertical weight of a tile row is the same for all 32 columns, so lane
+          // i computes it for row i (and how many source rows lie before it) once per item; the
+          // rows then take it with a shuffle instead of each lane redoing the integer walk.
+          // Rows past the box get a NaN weight: their sample compares false.
+          [[maybe_unused]] float wl = 0.f;
+          [[maybe_unused]] unsigned advmask = 0u;
+          if (kWalk == 1) {
+            const int t = remy + lane * step;          // < 2^24: exact in fp32
+            int q = __float2int_rd(static_cast<float>(t) * invDy);
+            int rem = t - q * Dy;
+            if (rem < 0) {
+              --q;
+              rem += Dy;
+            } else if (rem >= Dy) {
+              ++q;
+              rem -= Dy;
+            }
+            wl = lane < cnt ? static_cast<float>(rem) * invDy : __int_as_float(0x7fc00000);
+            // bit i: the source row advances between tile rows i and i + 1 (Dy > step: by one)
+            advmask = __ballot_sync(0xffffffffu, __shfl_down_sync(0xffffffffu, q, 1) != q);
+          }
           auto walk = [&](auto aligned_tag, auto deep_tag) {
             constexpr bool kAligned = decltype(aligned_tag)::value;
             constexpr bool kDeep = decltype(deep_tag)::value;
@@ -467,14 +529,26 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
             int sh = kAligned ? 0 : ((a0 + ra * rw15) & 15);   // row address mod 16 in HBM
 #pragma unroll
             for (int i = 0; i < kTileRows; ++i) {
-              const float v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
-              if (v >= thr && i < cnt)
-                asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + static_cast<uint32_t>(sh)), "r"(one));
+              bool adv;
+              float v;
+              if (kWalk == 1) {
+                v = fmaf(__shfl_sync(0xffffffffu, wl, i), dh, ht);
+                if (v >= thr)
+                  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + static_cast<uint32_t>(sh)), "r"(one));
+                adv = (advmask >> i) & 1u;      // warp-uniform, applied as a predicate
+              } else {
+                v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
+                if (v >= thr && i < cnt)
+                  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + static_cast<uint32_t>(sh)), "r"(one));
+                remy += step;
+                adv = remy >= Dy;               // warp-uniform, applied as a predicate
+                remy = adv ? remy - Dy : remy;
+              }
+              if (kValues) {
+                if (colvalid && i < cnt) vout[static_cast<size_t>(i) * RW] = v;
+              }
               addr += static_cast<uint32_t>(pitch);
               if (!kAligned) sh = (sh + rw15) & 15;
-              remy += step;
-              const bool adv = remy >= Dy;   // warp-uniform, applied as a predicate
-              remy = adv ? remy - Dy : remy;
               ht = adv ? hb : ht;
               hb = adv ? q2 : hb;
               q2 = adv ? q3 : q2;
@@ -521,6 +595,9 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
           const float v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
           if (v >= 0.5f && colvalid)
             asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + static_cast<uint32_t>(sh)), "r"(1u));
+          if (kValues) {
+            if (colvalid) vout[static_cast<size_t>(r - ra) * RW] = v;
+          }
           addr += static_cast<uint32_t>(pitch);
           sh = (sh + rw15) & 15;
           remy += stepRy;
@@ -551,7 +628,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
       // ---- store the tile: lane r owns the bulk copy of row r (its 16-byte aligned body)
       const bool mine = lane < kk;
       const int len = pw * N;
-      if (mine && !(p.flags & 0x400)) {
+      if (mine && !MRX_FLAG(p, 0x400)) {
         unsigned char *g = g0 + static_cast<size_t>(lane) * RW;
         const int a = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15u);
         unsigned char *s = s_buf + lane * pitch + a;
@@ -566,7 +643,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
       // ---- unaligned shapes: the <= 15 head and <= 15 tail bytes of every row, one byte per
       // lane (generic-proxy copies; the bulk copies above only read the buffer)
       if (((reinterpret_cast<uintptr_t>(g0) | RW | static_cast<unsigned>(len)) & 15u) != 0u &&
-          !(p.flags & 0x400)) {
+          !MRX_FLAG(p, 0x400)) {
         for (int r = 0; r < kk; ++r) {
           unsigned char *g = g0 + static_cast<size_t>(r) * RW;
           const int a = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15u);
@@ -600,15 +677,18 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     if (!more) break;
     slot = nslot;
   }
+  team_bar(bar_id, kTeamThreads);   // the decoding lane's last ticket precedes the retirement
+  retire();
   PROF_MARK(5)
   PROF_FLUSH
 }
 
 }  // namespace team
 
-template <int kTeams, int kTeamWarps, int kTileRows>
-static int launch_team_cfg(const ExpandParams &prm, int sms, int max_optin, int want_buf, cudaStream_t st) {
+template <int kTeams, int kTeamWarps, int kTileRows, bool kValues, int kWalk>
+static int launch_team_cfg(const ExpandParams &prm, const DevInfo &dev, int want_buf, cudaStream_t st) {
   using namespace team;
+  const int max_optin = dev.max_smem_optin;
   constexpr size_t kStatic = 256 + static_cast<size_t>(kTeams) * (kCand + 48);   // static __shared__ of the kernel
   const size_t fixed = static_cast<size_t>(kTeams) * kCand * sizeof(TEntry) +
                        static_cast<size_t>(kTeams) * 2 * sizeof(TJob) +
@@ -626,13 +706,14 @@ static int launch_team_cfg(const ExpandParams &prm, int sms, int max_optin, int 
   if (want_buf > 0 && want_buf < buf) buf = want_buf & ~127;
   if (buf < need) buf = need;
   const size_t smem = static_cast<size_t>(kTeams) * buf + fixed - kStatic;
-  auto kern = mask_expand_team_kernel<kTeams, kTeamWarps, kTileRows>;
-  MRX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem)));
-  // the tile counter starts at zero for every launch (stream-ordered; mrx_unmold_prologue
-  // also resets it, but the kernel must not depend on having been preceded by it)
-  MRX_CUDA(cudaMemsetAsync(prm.job_counter, 0, sizeof(unsigned int), st));
-  kern<<<sms, kTeams * kTeamWarps * 32, smem, st>>>(prm, buf);
+  auto kern = mask_expand_team_kernel<kTeams, kTeamWarps, kTileRows, kValues, kWalk>;
+  static SmemCache cache;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), &cache, dev.device,
+                                   static_cast<int>(smem)))
+    return rc;
+  // the two scheduler words are zero here: the caller zeroed them once and every launch
+  // (and mrx_unmold_prologue) leaves them zeroed
+  kern<<<dev.sms, kTeams * kTeamWarps * 32, smem, st>>>(prm, buf);
   MRX_LAUNCH_CHECK("mask_expand_team_kernel");
   return MRX_OK;
 }
@@ -645,41 +726,39 @@ extern "C" int mrx_debug_team_profile(long long *host_dst, int count) {
 }
 #endif
 
-// MRX_EXPAND_TEAMS="<teams>x<warps>x<rows>" selects one of the compiled shapes (development sweep)
-int launch_expand_team(const ExpandParams &prm, int sms, int max_optin, int want_buf, cudaStream_t st) {
-  int teams = 6, warps = 5, rows = 10;
+// The shipped shape: 6 teams x 5 warps, 10-row tiles (profiles/README.md has the sweep).
+int launch_expand_team(const ExpandParams &prm, const DevInfo &dev, int want_buf, cudaStream_t st) {
+  if (prm.mw > 30) return MRX_E_UNSUPPORTED;   // caller falls back to the generic kernel
+  if (prm.values != nullptr) return launch_team_cfg<6, 5, 10, true, MRX_DEFAULT_WALK>(prm, dev, want_buf, st);
+#ifdef MRX_DEV
+  // development sweep: MRX_EXPAND_TEAMS="<teams>x<warps>x<rows>[w<walk>]"
+  int teams = 6, warps = 5, rows = 10, walk = MRX_DEFAULT_WALK;
   if (const char *e = getenv("MRX_EXPAND_TEAMS")) {
-    int a = 0, b = 0, c = 0;
-    if (sscanf(e, "%dx%dx%d", &a, &b, &c) == 3) {
+    int a = 0, b = 0, c = 0, w = MRX_DEFAULT_WALK;
+    if (sscanf(e, "%dx%dx%dw%d", &a, &b, &c, &w) >= 3) {
       teams = a;
       warps = b;
       rows = c;
+      walk = w;
     }
   }
-  if (prm.mw > 30) return MRX_E_UNSUPPORTED;   // caller falls back to the generic kernel
-#define MRX_TEAM_CASE(T, W, R) \
-  if (teams == T && warps == W && rows == R) return launch_team_cfg<T, W, R>(prm, sms, max_optin, want_buf, st)
+#define MRX_TEAM_CASE(T, W, R)                                                                  \
+  if (teams == T && warps == W && rows == R)                                                    \
+    return walk ? launch_team_cfg<T, W, R, false, 1>(prm, dev, want_buf, st)                    \
+                : launch_team_cfg<T, W, R, false, 0>(prm, dev, want_buf, st)
   MRX_TEAM_CASE(4, 7, 16);
-  MRX_TEAM_CASE(4, 5, 16);
-  MRX_TEAM_CASE(4, 6, 16);
-  MRX_TEAM_CASE(4, 8, 16);
   MRX_TEAM_CASE(5, 5, 12);
   MRX_TEAM_CASE(5, 6, 12);
   MRX_TEAM_CASE(6, 4, 10);
   MRX_TEAM_CASE(6, 5, 10);
-  MRX_TEAM_CASE(7, 4, 8);
+  MRX_TEAM_CASE(6, 5, 11);
   MRX_TEAM_CASE(7, 4, 9);
-  MRX_TEAM_CASE(6, 5, 8);
-  MRX_TEAM_CASE(7, 3, 9);
-  MRX_TEAM_CASE(2, 14, 32);
-  MRX_TEAM_CASE(2, 10, 32);
-  MRX_TEAM_CASE(2, 8, 32);
-  MRX_TEAM_CASE(2, 16, 32);
-  MRX_TEAM_CASE(3, 9, 21);
-  MRX_TEAM_CASE(3, 7, 21);
 #undef MRX_TEAM_CASE
   set_error("mrx_mask_expand: MRX_EXPAND_TEAMS=%dx%dx%d is not a compiled shape", teams, warps, rows);
   return MRX_E_INVALID;
+#else
+  return launch_team_cfg<6, 5, 10, false, MRX_DEFAULT_WALK>(prm, dev, want_buf, st);
+#endif
 }
 
 }  // namespace mrx

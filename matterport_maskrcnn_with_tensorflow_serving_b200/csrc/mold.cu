@@ -40,11 +40,26 @@ __device__ __forceinline__ LinCoef cv_lin_coef(int d, double scale, int n_src, b
   return c;
 }
 
+// Image blockIdx.y of a batch: sources of any size at src + src_off[b] (sizes in src_hw[b]),
+// destinations dh x dw each, densely packed.  src_off == nullptr: one image, sizes by value.
 __global__ void __launch_bounds__(kMoldThreads)
-cv2_resize_kernel(const unsigned char *__restrict__ src, int sh, int sw,
-                  unsigned char *__restrict__ dst, int dh, int dw, double scale_y,
-                  double scale_x, int area_fast_2x) {
+cv2_resize_kernel(const unsigned char *__restrict__ src, const long long *__restrict__ src_off,
+                  const int *__restrict__ src_hw, int sh, int sw,
+                  unsigned char *__restrict__ dst, int dh, int dw) {
   const long long total = static_cast<long long>(dh) * dw;
+  if (src_off != nullptr) {
+    const int b = blockIdx.y;
+    src += src_off[b];
+    sh = src_hw[2 * b];
+    sw = src_hw[2 * b + 1];
+    dst += static_cast<size_t>(b) * total * 3;
+  }
+  // cv::resize: inv_scale = dsize/ssize (double) ; hal::resize: scale = 1./inv_scale
+  const double scale_x = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dw), static_cast<double>(sw)));
+  const double scale_y = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dh), static_cast<double>(sh)));
+  // INTER_LINEAR with an exact 2x shrink in both axes is computed as INTER_AREA (2x2 box)
+  const double eps = 2.220446049250313e-16;
+  const bool area_fast_2x = fabs(scale_x - 2.0) < eps && fabs(scale_y - 2.0) < eps;
   for (long long i = static_cast<long long>(blockIdx.x) * kMoldThreads + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kMoldThreads) {
     const int dy = static_cast<int>(i / dw);
@@ -90,6 +105,7 @@ __device__ __forceinline__ ZoomCoef zoom_coef(int k, double zoom) {
   return z;
 }
 
+// Image blockIdx.y of a batch of equally sized sources (densely packed) -> equally sized outputs.
 template <typename TOut>
 __global__ void __launch_bounds__(kMoldThreads)
 mold_image_kernel(const unsigned char *__restrict__ src, int sh, int sw, int new_h, int new_w,
@@ -97,6 +113,9 @@ mold_image_kernel(const unsigned char *__restrict__ src, int sh, int sw, int new
                   double m0, double m1, double m2, TOut *__restrict__ out,
                   unsigned char *__restrict__ out_u8) {
   const long long total = static_cast<long long>(out_h) * out_w;
+  src += static_cast<size_t>(blockIdx.y) * sh * sw * 3;
+  out += static_cast<size_t>(blockIdx.y) * total * 3;
+  if (out_u8) out_u8 += static_cast<size_t>(blockIdx.y) * total * 3;
   const bool scaled = (new_h != sh) || (new_w != sw);
   const double mean[3] = {m0, m1, m2};
   for (long long i = static_cast<long long>(blockIdx.x) * kMoldThreads + threadIdx.x; i < total;
@@ -154,30 +173,39 @@ static unsigned grid_for(long long total, int threads) {
 
 using namespace mrx;
 
+static int cv2_resize_launch(const unsigned char *d_src, const long long *d_src_off,
+                             const int *d_src_hw, int src_h, int src_w, unsigned char *d_dst,
+                             int B, int dst_h, int dst_w, void *stream) {
+  const long long total = static_cast<long long>(dst_h) * dst_w;
+  dim3 grid(grid_for(total, kMoldThreads), B);
+  cv2_resize_kernel<<<grid, kMoldThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_src, d_src_off, d_src_hw, src_h, src_w, d_dst, dst_h, dst_w);
+  MRX_LAUNCH_CHECK("cv2_resize_kernel");
+  return MRX_OK;
+}
+
 extern "C" int mrx_cv2_resize_u8c3(const unsigned char *d_src, int src_h, int src_w,
                                    unsigned char *d_dst, int dst_h, int dst_w, void *stream) {
   MRX_CHECK_ARG(d_src && d_dst, "mrx_cv2_resize_u8c3: null pointer");
   MRX_CHECK_ARG(src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1,
                 "mrx_cv2_resize_u8c3: bad sizes %dx%d -> %dx%d", src_h, src_w, dst_h, dst_w);
-  // cv::resize: inv_scale = dsize/ssize (double) ; hal::resize: scale = 1./inv_scale
-  const double inv_x = static_cast<double>(dst_w) / src_w;
-  const double inv_y = static_cast<double>(dst_h) / src_h;
-  const double scale_x = 1.0 / inv_x, scale_y = 1.0 / inv_y;
-  const int isx = static_cast<int>(nearbyint(scale_x)), isy = static_cast<int>(nearbyint(scale_y));
-  const double eps = 2.220446049250313e-16;
-  const int area2 = (fabs(scale_x - isx) < eps && fabs(scale_y - isy) < eps && isx == 2 && isy == 2);
-  const long long total = static_cast<long long>(dst_h) * dst_w;
-  cv2_resize_kernel<<<grid_for(total, kMoldThreads), kMoldThreads, 0,
-                      static_cast<cudaStream_t>(stream)>>>(d_src, src_h, src_w, d_dst, dst_h,
-                                                           dst_w, scale_y, scale_x, area2);
-  MRX_LAUNCH_CHECK("cv2_resize_kernel");
-  return MRX_OK;
+  return cv2_resize_launch(d_src, nullptr, nullptr, src_h, src_w, d_dst, 1, dst_h, dst_w, stream);
 }
 
-extern "C" int mrx_mold_image(const unsigned char *d_src, int src_h, int src_w, int new_h,
-                              int new_w, int top, int left, int out_h, int out_w,
-                              const double *mean_pixel, int out_dtype, void *d_out,
-                              unsigned char *d_molded_u8, void *stream) {
+extern "C" int mrx_cv2_resize_u8c3_batch(const unsigned char *d_src, const long long *d_src_off,
+                                         const int *d_src_hw, unsigned char *d_dst, int B,
+                                         int dst_h, int dst_w, void *stream) {
+  MRX_CHECK_ARG(d_src && d_src_off && d_src_hw && d_dst, "mrx_cv2_resize_u8c3_batch: null pointer");
+  MRX_CHECK_ARG(B >= 0 && B <= 65535 && dst_h >= 1 && dst_w >= 1,
+                "mrx_cv2_resize_u8c3_batch: bad sizes B=%d dst %dx%d", B, dst_h, dst_w);
+  if (B == 0) return MRX_OK;
+  return cv2_resize_launch(d_src, d_src_off, d_src_hw, 0, 0, d_dst, B, dst_h, dst_w, stream);
+}
+
+static int mold_launch(const unsigned char *d_src, int B, int src_h, int src_w, int new_h,
+                       int new_w, int top, int left, int out_h, int out_w,
+                       const double *mean_pixel, int out_dtype, void *d_out,
+                       unsigned char *d_molded_u8, void *stream) {
   MRX_CHECK_ARG(d_src && d_out && mean_pixel, "mrx_mold_image: null pointer");
   MRX_CHECK_ARG(src_h >= 1 && src_w >= 1 && new_h >= 1 && new_w >= 1 && out_h >= 1 && out_w >= 1,
                 "mrx_mold_image: bad sizes");
@@ -186,20 +214,39 @@ extern "C" int mrx_mold_image(const unsigned char *d_src, int src_h, int src_w, 
                 new_h, new_w, out_h, out_w);
   MRX_CHECK_ARG(out_dtype == MRX_F32 || out_dtype == MRX_F64, "mrx_mold_image: out_dtype %d",
                 out_dtype);
+  MRX_CHECK_ARG(B >= 0 && B <= 65535, "mrx_mold_image_batch: B=%d", B);
+  if (B == 0) return MRX_OK;
   // scipy.ndimage.zoom(grid_mode=True): zoom = in / out per axis (float64)
   const double zoom_y = static_cast<double>(src_h) / new_h;
   const double zoom_x = static_cast<double>(src_w) / new_w;
   const long long total = static_cast<long long>(out_h) * out_w;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(grid_for(total, kMoldThreads), B);
   if (out_dtype == MRX_F64) {
-    mold_image_kernel<double><<<grid_for(total, kMoldThreads), kMoldThreads, 0, st>>>(
+    mold_image_kernel<double><<<grid, kMoldThreads, 0, st>>>(
         d_src, src_h, src_w, new_h, new_w, top, left, out_h, out_w, zoom_y, zoom_x,
         mean_pixel[0], mean_pixel[1], mean_pixel[2], static_cast<double *>(d_out), d_molded_u8);
   } else {
-    mold_image_kernel<float><<<grid_for(total, kMoldThreads), kMoldThreads, 0, st>>>(
+    mold_image_kernel<float><<<grid, kMoldThreads, 0, st>>>(
         d_src, src_h, src_w, new_h, new_w, top, left, out_h, out_w, zoom_y, zoom_x,
         mean_pixel[0], mean_pixel[1], mean_pixel[2], static_cast<float *>(d_out), d_molded_u8);
   }
   MRX_LAUNCH_CHECK("mold_image_kernel");
   return MRX_OK;
+}
+
+extern "C" int mrx_mold_image(const unsigned char *d_src, int src_h, int src_w, int new_h,
+                              int new_w, int top, int left, int out_h, int out_w,
+                              const double *mean_pixel, int out_dtype, void *d_out,
+                              unsigned char *d_molded_u8, void *stream) {
+  return mold_launch(d_src, 1, src_h, src_w, new_h, new_w, top, left, out_h, out_w, mean_pixel,
+                     out_dtype, d_out, d_molded_u8, stream);
+}
+
+extern "C" int mrx_mold_image_batch(const unsigned char *d_src, int B, int src_h, int src_w,
+                                    int new_h, int new_w, int top, int left, int out_h,
+                                    int out_w, const double *mean_pixel, int out_dtype,
+                                    void *d_out, unsigned char *d_molded_u8, void *stream) {
+  return mold_launch(d_src, B, src_h, src_w, new_h, new_w, top, left, out_h, out_w, mean_pixel,
+                     out_dtype, d_out, d_molded_u8, stream);
 }

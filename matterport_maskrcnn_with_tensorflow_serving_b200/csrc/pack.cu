@@ -1,21 +1,28 @@
-// pack.cu -- bit-packed mask output (compact mask transport).
+// pack.cu -- bit-pack an existing [H,W,N] byte canvas (compact mask transport).
 // An EXTENSION, not the reference layout: unmold_detections returns bool [H,W,N] (1 byte per
 // element, 105 MB per 1024x1024x100 image) and this is what mrx_mask_expand writes.  Callers
 // that can take packed masks get   packed[n][y][xb] = np.packbits(masks[:, :, n], axis=1)
 // (8 pixels per byte, most significant bit first, rows padded to whole bytes): 8x less
 // device -> host traffic; np.unpackbits(packed, axis=-1, count=W).transpose(1, 2, 0) restores
-// the reference array exactly.
+// the reference array exactly.  (mrx_mask_expand_packed, expand_bits.cu, produces the same
+// bytes without ever writing the byte canvas; this kernel serves callers that hold one.)
 //
-// One CTA = 256 consecutive pixels of one canvas row: their 256*N canvas bytes are contiguous
-// (N innermost) and are staged into shared memory; then, per instance n, warp w reads the bytes
-// of its 32 pixels (stride N: conflict-free for N = 100), ballots them into a 32-bit word,
-// reverses it into packbits order and stores 4 bytes; the 8 warps of the CTA fill one 32-byte
-// sector of packed[n][y][.] per instance.  HBM-read bound: N bytes per pixel in, N/8 out.
+// HBM-read bound: N bytes per pixel in, N/8 out.  One CTA = 256 consecutive pixels of one canvas
+// row: their 256*N canvas bytes are contiguous (N innermost) and are staged into shared memory
+// with 16-byte loads, several in flight per thread.  The transpose to bit planes is byte
+// arithmetic, no ballots: a thread takes 8 consecutive pixels x 4 consecutive instances -- eight
+// 32-bit shared-memory words, one per pixel, each holding the 0/1 bytes of the four instances --
+// and folds them with   acc |= (word & 0x01010101) << (7 - k)   into four output bytes, one
+// per instance plane.  Lanes are laid out 4 pixel groups x 8 instance quads so that the eight
+// words of a step fall into 32 different banks (pixel-group stride 8*N bytes = 8 banks at
+// N = 100, instance-quad stride one bank).  Shapes with N % 4 != 0 or rows that are not
+// 4-byte aligned take the same walk one instance (one byte) at a time.
 #include "common.cuh"
 
 namespace mrx {
 
 constexpr int kPackThreads = 256;
+constexpr int kPackPixels = 256;
 
 __global__ void __launch_bounds__(kPackThreads)
 pack_masks_kernel(const unsigned char *__restrict__ canvas, const long long *__restrict__ canvas_off,
@@ -25,48 +32,83 @@ pack_masks_kernel(const unsigned char *__restrict__ canvas, const long long *__r
   const int b = blockIdx.z;
   const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
   const int y = blockIdx.y;
-  const int x0 = blockIdx.x * kPackThreads;
+  const int x0 = blockIdx.x * kPackPixels;
   const int N = counts[b];
   if (y >= H || x0 >= W || N <= 0) return;
-  const int npx = min(kPackThreads, W - x0);
+  const int npx = min(kPackPixels, W - x0);
   const int t = threadIdx.x;
-  const int lane = t & 31, warp = t >> 5;
 
-  // stage the npx * N bytes of these pixels: 16-byte loads when the run is 16-byte aligned
+  // ---- stage the npx * N bytes of these pixels at their global address mod 16
   const unsigned char *src = canvas + canvas_off[b] + (static_cast<long long>(y) * W + x0) * N;
   const int nbytes = npx * N;
-  if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u) {
-    const int n16 = nbytes >> 4;
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+  const int a = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
+  {
+    // every canvas slot starts 16-byte aligned and holds whole 16-byte words (see mrx.h): the
+    // first and last word of the run may include neighbouring pixels' bytes, never unmapped memory
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src - a);
     uint4 *d4 = reinterpret_cast<uint4 *>(smem);
-    for (int i = t; i < n16; i += kPackThreads) d4[i] = __ldg(s4 + i);
-    for (int i = (n16 << 4) + t; i < nbytes; i += kPackThreads) smem[i] = src[i];
-  } else {
-    for (int i = t; i < nbytes; i += kPackThreads) smem[i] = src[i];
+    const int n16 = (a + nbytes + 15) >> 4;
+    int i = t;
+    for (; i + 3 * kPackThreads < n16; i += 4 * kPackThreads) {
+      const uint4 v0 = __ldg(s4 + i), v1 = __ldg(s4 + i + kPackThreads),
+                  v2 = __ldg(s4 + i + 2 * kPackThreads), v3 = __ldg(s4 + i + 3 * kPackThreads);
+      d4[i] = v0;
+      d4[i + kPackThreads] = v1;
+      d4[i + 2 * kPackThreads] = v2;
+      d4[i + 3 * kPackThreads] = v3;
+    }
+    for (; i < n16; i += kPackThreads) d4[i] = __ldg(s4 + i);
   }
   __syncthreads();
+  const unsigned char *px0 = smem + a;   // byte of (pixel x0, instance 0)
 
-  const int wb = (W + 7) >> 3;                       // bytes per packed row
-  const int px = warp * 32 + lane;                   // this lane's pixel inside the CTA
-  const bool valid = px < npx;
-  const int bx = (x0 >> 3) + warp * 4;               // first packed byte of this warp's 32 pixels
-  const int nb = min(4, wb - bx);                    // bytes of it inside the row (<= 0: none)
-  unsigned char *dst = packed + packed_off[b] + (static_cast<long long>(y) * wb + bx);
+  const int wb = (W + 7) >> 3;                        // bytes per packed row
   const long long plane = static_cast<long long>(H) * wb;
-  const unsigned char *mine = smem + static_cast<size_t>(px) * N;
-  // one 4-byte store per (warp, instance) when the warp's four bytes exist and every plane's
-  // copy of them is 4-byte aligned; byte stores otherwise (row ends, odd row pitches)
-  const bool word_ok = nb == 4 && ((reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(plane)) & 3u) == 0u;
-  for (int n = 0; n < N; ++n) {
-    const unsigned bit = valid ? (mine[n] != 0) : 0u;
-    const unsigned bal = __ballot_sync(0xffffffffu, bit);
-    // ballot bit l = pixel l; packbits puts pixel 0 in the most significant bit of byte 0
-    const unsigned rev = __brev(bal);                // bit 31 = pixel 0
-    if (word_ok) {
-      // memory order byte0..byte3 = rev bits 31..24, 23..16, 15..8, 7..0
-      if (lane == 0) *reinterpret_cast<unsigned *>(dst + n * plane) = __byte_perm(rev, 0u, 0x0123);
-    } else if (lane < nb) {
-      dst[n * plane + lane] = static_cast<unsigned char>(rev >> (24 - 8 * lane));
+  unsigned char *dst = packed + packed_off[b] + static_cast<long long>(y) * wb + (x0 >> 3);
+  const int ngroups = (npx + 7) >> 3;                 // 8-pixel groups = output bytes per plane
+  const int lane = t & 31, warp = t >> 5;
+  const int gs = lane >> 3, qs = lane & 7;            // 4 pixel groups x 8 instance slots per warp step
+  if (((N | a) & 3) == 0) {
+    // ---- four instances at a time: 32-bit words
+    const int nquads = N >> 2;
+    const int qblocks = (nquads + 7) >> 3;
+    const int gblocks = (ngroups + 3) >> 2;
+    for (int step = warp; step < gblocks * qblocks; step += kPackThreads / 32) {
+      const int gb = step / qblocks, qb = step - gb * qblocks;
+      const int g = gb * 4 + gs, q = qb * 8 + qs;
+      if (g >= ngroups || q >= nquads) continue;
+      const uint32_t *wp = reinterpret_cast<const uint32_t *>(px0 + static_cast<size_t>(8 * g) * N) + q;
+      const int live = min(8, npx - 8 * g);           // pixels of the group inside the row
+      const int stride = N >> 2;
+      uint32_t acc = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t w = (k < live) ? wp[k * stride] : 0u;
+        acc |= (w & 0x01010101u) << (7 - k);
+      }
+      unsigned char *o = dst + g + static_cast<long long>(4 * q) * plane;
+      o[0] = static_cast<unsigned char>(acc);
+      o[plane] = static_cast<unsigned char>(acc >> 8);
+      o[2 * plane] = static_cast<unsigned char>(acc >> 16);
+      o[3 * plane] = static_cast<unsigned char>(acc >> 24);
+    }
+  } else {
+    // ---- any N, any alignment: one instance per slot
+    const int nblocks = (N + 7) >> 3;
+    const int gblocks = (ngroups + 3) >> 2;
+    for (int step = warp; step < gblocks * nblocks; step += kPackThreads / 32) {
+      const int gb = step / nblocks, nb = step - gb * nblocks;
+      const int g = gb * 4 + gs, n = nb * 8 + qs;
+      if (g >= ngroups || n >= N) continue;
+      const unsigned char *bp = px0 + static_cast<size_t>(8 * g) * N + n;
+      const int live = min(8, npx - 8 * g);
+      unsigned acc = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned v = (k < live) ? bp[k * N] : 0u;
+        acc |= (v & 1u) << (7 - k);
+      }
+      dst[g + static_cast<long long>(n) * plane] = static_cast<unsigned char>(acc);
     }
   }
 }
@@ -84,16 +126,17 @@ extern "C" int mrx_pack_masks(const unsigned char *d_canvas, const long long *d_
                 "mrx_pack_masks: bad sizes B=%d R=%d", B, R);
   if (B == 0 || max_h == 0 || max_w == 0) return MRX_OK;
   MRX_CHECK_SUPPORTED(max_h <= 65535, "mrx_pack_masks: image taller than 65535 rows");
-  int dev = 0, max_optin = 0;
-  MRX_CUDA(cudaGetDevice(&dev));
-  MRX_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t smem = static_cast<size_t>(kPackThreads) * R + 16;
-  MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(max_optin),
+  DevInfo dev;
+  if (int rc = current_device_info(&dev)) return rc;
+  const size_t smem = static_cast<size_t>(kPackPixels) * R + 32;
+  MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(dev.max_smem_optin),
                       "mrx_pack_masks: R=%d needs %zu B of shared memory (limit %d)", R, smem,
-                      max_optin);
-  MRX_CUDA(cudaFuncSetAttribute(pack_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem)));
-  dim3 grid((max_w + kPackThreads - 1) / kPackThreads, max_h, B);
+                      dev.max_smem_optin);
+  static SmemCache cache;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(pack_masks_kernel), &cache,
+                                   dev.device, static_cast<int>(smem)))
+    return rc;
+  dim3 grid((max_w + kPackPixels - 1) / kPackPixels, max_h, B);
   pack_masks_kernel<<<grid, kPackThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       d_canvas, d_canvas_off, d_counts, d_geom, d_packed, d_packed_off);
   MRX_LAUNCH_CHECK("pack_masks_kernel");

@@ -77,7 +77,10 @@ unmold_prologue_kernel(const T *__restrict__ det, int R, int C,
   if (tid == 0) {
     s_first_zero = R;
     s_status = 0;
-    if (b == 0 && job_counter != nullptr) *job_counter = 0u;
+    if (b == 0 && job_counter != nullptr) {   // scheduler words of mrx_mask_expand*: ticket, retired
+      job_counter[0] = 0u;
+      job_counter[1] = 0u;
+    }
   }
   __syncthreads();
 
@@ -540,36 +543,14 @@ mask_expand_kernel(const ExpandParams p) {
     }
     if (wrote) clean = 0;
   }
-  if (tid == 0) bulk_wait_all<0>();
-}
-
-// =====================================================================================
-// test hook: pre-threshold values of one resized tile, same sampling code
-// =====================================================================================
-__global__ void resize_tile_kernel(const float *__restrict__ tile, int mh, int mw, int bh,
-                                   int bw, float *__restrict__ out) {
-  const int y = blockIdx.x;
-  const int Dy = 2 * bh;
-  const int Ay = mh * (2 * y + 1) - bh;
-  const int j0 = floor_div(Ay, Dy);
-  const float wy = __fdiv_rn(static_cast<float>(Ay - j0 * Dy), static_cast<float>(Dy));
-  extern __shared__ float s_row[];   // mw + 2
-  for (int i = threadIdx.x; i < mw + 2; i += blockDim.x) {
-    float v = 0.f;
-    if (i >= 1 && i <= mw) {
-      const float top = (j0 < 0) ? 0.f : tile[j0 * mw + (i - 1)];
-      const float bot = (j0 + 1 > mh - 1) ? 0.f : tile[(j0 + 1) * mw + (i - 1)];
-      v = fmaf(wy, bot - top, top);
+  if (tid == 0) {
+    bulk_wait_all<0>();
+    // the last CTA to retire leaves both scheduler words at zero for the next launch
+    __threadfence();
+    if (atomicAdd(p.job_counter + 1, 1u) == gridDim.x - 1u) {
+      p.job_counter[0] = 0u;
+      p.job_counter[1] = 0u;
     }
-    s_row[i] = v;
-  }
-  __syncthreads();
-  const float inv_2bw = __fdiv_rn(1.0f, static_cast<float>(2 * bw));
-  for (int x = threadIdx.x; x < bw; x += blockDim.x) {
-    const SrcCoord sc = src_coord(x, mw, bw, inv_2bw);
-    const float a = s_row[sc.i0 + 1];
-    const float bq = s_row[sc.i0 + 2];
-    out[static_cast<size_t>(y) * bw + x] = fmaf(sc.w, bq - a, a);
   }
 }
 
@@ -591,7 +572,7 @@ static int check_mask_dims(int mh, int mw) {
 extern "C" int mrx_unmold_prologue(const void *d_detections, int det_dtype, int B, int R, int C,
                                    int mw, const int *d_geom, int *d_boxes, int *d_class_ids,
                                    void *d_scores, int *d_src_index, int *d_box_aux,
-                                   int *d_counts, int *d_status, unsigned int *d_job_counter,
+                                   int *d_counts, int *d_status, unsigned int *d_sched,
                                    void *stream) {
   MRX_CHECK_ARG(d_detections && d_geom && d_boxes && d_class_ids && d_scores && d_src_index &&
                     d_box_aux && d_counts && d_status,
@@ -607,12 +588,12 @@ extern "C" int mrx_unmold_prologue(const void *d_detections, int det_dtype, int 
     unmold_prologue_kernel<double><<<B, kPrologueThreads, 0, st>>>(
         static_cast<const double *>(d_detections), R, C, d_geom, d_boxes, d_class_ids,
         static_cast<double *>(d_scores), d_src_index, reinterpret_cast<BoxAux *>(d_box_aux), mw,
-        d_counts, d_status, d_job_counter);
+        d_counts, d_status, d_sched);
   } else {
     unmold_prologue_kernel<float><<<B, kPrologueThreads, 0, st>>>(
         static_cast<const float *>(d_detections), R, C, d_geom, d_boxes, d_class_ids,
         static_cast<float *>(d_scores), d_src_index, reinterpret_cast<BoxAux *>(d_box_aux), mw,
-        d_counts, d_status, d_job_counter);
+        d_counts, d_status, d_sched);
   }
   MRX_LAUNCH_CHECK("unmold_prologue_kernel");
   return MRX_OK;
@@ -644,29 +625,25 @@ extern "C" int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype, int B,
   return MRX_OK;
 }
 
-extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
-                               const int *d_counts, const int *d_geom,
-                               const long long *d_canvas_off,
-                               unsigned char *d_canvas, int B, int R, int mh, int mw,
-                               int chunk_bytes, int ctas_per_sm, unsigned int *d_job_counter,
-                               void *stream) {
+static int mask_expand_impl(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
+                            const int *d_counts, const int *d_geom, const long long *d_canvas_off,
+                            unsigned char *d_canvas, float *d_values, int B, int R, int mh, int mw,
+                            int chunk_bytes, int ctas_per_sm, unsigned int *d_sched,
+                            void *stream) {
   MRX_CHECK_ARG(d_tiles && d_boxes && d_box_aux && d_counts && d_geom && d_canvas_off &&
-                    d_canvas && d_job_counter,
+                    d_canvas && d_sched,
                 "mrx_mask_expand: null pointer");
   MRX_CHECK_ARG(B >= 0 && B <= MRX_MAX_BATCH && R >= 1, "mrx_mask_expand: bad sizes B=%d R=%d",
                 B, R);
   if (int rc = check_mask_dims(mh, mw)) return rc;
-  const int want_buf = chunk_bytes;   // generation 6: upper bound of a team's tile buffer, 0 = auto
+  const int want_buf = chunk_bytes;   // team kernel: upper bound of a team's tile buffer, 0 = auto
   if (chunk_bytes == 0) chunk_bytes = 25600;
   MRX_CHECK_ARG(chunk_bytes >= 1024 && (chunk_bytes % 16) == 0,
                 "mrx_mask_expand: chunk_bytes %d must be a multiple of 16, >= 1024", chunk_bytes);
   if (B == 0) return MRX_OK;
 
-  int dev = 0;
-  MRX_CUDA(cudaGetDevice(&dev));
-  int sms = 0, max_optin = 0;
-  MRX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  MRX_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  DevInfo dev;
+  if (int rc = current_device_info(&dev)) return rc;
 
   ExpandParams prm;
   prm.tiles = d_tiles;
@@ -676,55 +653,69 @@ extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const i
   prm.geom = d_geom;
   prm.canvas_off = d_canvas_off;
   prm.canvas = d_canvas;
-  prm.job_counter = d_job_counter;
+  prm.job_counter = d_sched;
+  prm.values = d_values;
   prm.B = B;
   prm.R = R;
   prm.mh = mh;
   prm.mw = mw;
   prm.chunk_bytes = chunk_bytes;
+  prm.flags = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the team kernel keeps a tile row in one warp's registers (mw + 2 <= 32 lanes); wider tiles
+  // and R too large for its tile buffers take the generic kernel
+  bool generic = mw > 30;
+#ifdef MRX_DEV
   {
     const char *f = getenv("MRX_EXPAND_FLAGS");
     prm.flags = f ? atoi(f) : 0;
+    const char *impl = getenv("MRX_EXPAND_IMPL");
+    if (impl != nullptr && strcmp(impl, "generic") == 0) generic = true;
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char *impl = getenv("MRX_EXPAND_IMPL");
-  auto is = [&](const char *name) { return impl != nullptr && strcmp(impl, name) == 0; };
-  // generations 4-6 keep a blended tile row in one warp's registers (mw + 2 <= 32 lanes);
-  // wider tiles take the generic kernel
-  bool use_v2 = is("v2") || mw > 30;
-  if (!use_v2) {
-    if (is("v4")) return launch_expand_ws4(prm, sms, max_optin, st);
-    const int rc = launch_expand_team(prm, sms, max_optin, want_buf, st);
+#endif
+  if (!generic) {
+    const int rc = launch_expand_team(prm, dev, want_buf, st);
     if (rc != MRX_E_UNSUPPORTED) return rc;
-    use_v2 = true;   // R too large for the tile buffers: generic kernel
   }
+  MRX_CHECK_SUPPORTED(d_values == nullptr,
+                      "mrx_mask_expand_values: shape outside the team kernel (R=%d, mw=%d)", R, mw);
   const size_t smem = static_cast<size_t>(chunk_bytes) +
                       static_cast<size_t>(kEMax) * 2 * mw * sizeof(float) +
                       static_cast<size_t>(kEMax) * sizeof(Entry) +
                       static_cast<size_t>(B + 1) * sizeof(int);
-  MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(max_optin),
+  MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(dev.max_smem_optin),
                       "mrx_mask_expand: %zu B shared memory > device limit %d (chunk_bytes too "
                       "large)",
-                      smem, max_optin);
-  MRX_CUDA(cudaFuncSetAttribute(mask_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem)));
+                      smem, dev.max_smem_optin);
+  static SmemCache cache;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(mask_expand_kernel), &cache,
+                                   dev.device, static_cast<int>(smem)))
+    return rc;
   int occ = 0;
   MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mask_expand_kernel,
                                                          kExpandThreads, smem));
   MRX_CHECK_SUPPORTED(occ >= 1, "mrx_mask_expand: kernel does not fit on an SM");
   if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
-  mask_expand_kernel<<<sms * occ, kExpandThreads, smem, st>>>(prm);
+  mask_expand_kernel<<<dev.sms * occ, kExpandThreads, smem, st>>>(prm);
   MRX_LAUNCH_CHECK("mask_expand_kernel");
   return MRX_OK;
 }
 
-extern "C" int mrx_resize_tile_f32(const float *d_tile, int mh, int mw, int bh, int bw,
-                                   float *d_out, void *stream) {
-  MRX_CHECK_ARG(d_tile && d_out, "mrx_resize_tile_f32: null pointer");
-  MRX_CHECK_ARG(bh >= 1 && bw >= 1 && bh <= 65535, "mrx_resize_tile_f32: bad box %dx%d", bh, bw);
-  if (int rc = check_mask_dims(mh, mw)) return rc;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  resize_tile_kernel<<<bh, 128, (mw + 2) * sizeof(float), st>>>(d_tile, mh, mw, bh, bw, d_out);
-  MRX_LAUNCH_CHECK("resize_tile_kernel");
-  return MRX_OK;
+extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
+                               const int *d_counts, const int *d_geom,
+                               const long long *d_canvas_off, unsigned char *d_canvas, int B,
+                               int R, int mh, int mw, int chunk_bytes, int ctas_per_sm,
+                               unsigned int *d_sched, void *stream) {
+  return mask_expand_impl(d_tiles, d_boxes, d_box_aux, d_counts, d_geom, d_canvas_off, d_canvas,
+                          nullptr, B, R, mh, mw, chunk_bytes, ctas_per_sm, d_sched, stream);
+}
+
+extern "C" int mrx_mask_expand_values(const float *d_tiles, const int *d_boxes,
+                                      const int *d_box_aux, const int *d_counts,
+                                      const int *d_geom, const long long *d_canvas_off,
+                                      unsigned char *d_canvas, float *d_values, int B, int R,
+                                      int mh, int mw, unsigned int *d_sched, void *stream) {
+  MRX_CHECK_ARG(d_values != nullptr, "mrx_mask_expand_values: null pointer");
+  return mask_expand_impl(d_tiles, d_boxes, d_box_aux, d_counts, d_geom, d_canvas_off, d_canvas,
+                          d_values, B, R, mh, mw, 0, 0, d_sched, stream);
 }

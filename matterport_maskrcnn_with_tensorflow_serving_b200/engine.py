@@ -12,7 +12,8 @@ every computation on the path is a libmrx kernel launched through ctypes.
 from __future__ import annotations
 
 import ctypes as C
-import math
+import sys
+import threading
 
 import numpy as np
 
@@ -58,6 +59,12 @@ class UnmoldEngine:
     allocated once; the canvas (bool [H,W,N] per image, N innermost) lives in one device
     buffer with a fixed-capacity slot per image (capacity H*W*R rounded up to 256 B) so
     that nothing on the path depends on a host read of the kept counts.
+
+    Thread safety: an engine is a set of device buffers plus the plan of the last batch; a
+    plan -> enqueue -> fetch sequence must not interleave with another thread's.  Callers
+    that share an engine hold `engine.lock` (an RLock) across the sequence -- `api_utils`
+    does.  `release()` frees the big buffers (canvas, packed output); they are re-allocated
+    on the next plan.
     """
 
     def __init__(self, max_batch, max_instances=100, mask_hw=(28, 28), num_classes=81,
@@ -90,22 +97,40 @@ class UnmoldEngine:
         self.d_tiles = torch.empty((B, R, self.mh, self.mw), dtype=torch.float32, device=dev)
         self.d_geom = torch.zeros((B, N.MRX_GEOM_INTS), dtype=i32, device=dev)
         self.d_canvas_off = torch.zeros((B,), dtype=torch.int64, device=dev)
-        self.d_job_counter = torch.zeros((1,), dtype=i32, device=dev)
+        # scheduler words of the expand kernels: zeroed once here, left zeroed by every launch
+        self.d_sched = torch.zeros((N.MRX_SCHED_WORDS,), dtype=i32, device=dev)
         self.d_canvas = None
+        self.d_packed = None
+        self.d_packed_off = None
+        self._packed_off_host = None
         self._geom_host = None
         self._offsets = None
         self._n_images = 0
+        self.lock = threading.RLock()
+        # pinned staging for fetch_meta (one D2H batch + one synchronisation per call)
+        self._h_meta = None
+
+    def release(self):
+        """Free the canvas and the packed-output buffer (the work buffers stay)."""
+        with self.lock:
+            self.d_canvas = None
+            self.d_packed = None
+            self._geom_host = None
+            self._offsets = None
+            self._packed_off_host = None
+            self._n_images = 0
 
     # ------------------------------------------------------------------ planning
-    def plan(self, geoms):
-        """Set the per-image geometry ([n,8] ints, see make_geom) and size the canvas."""
+    def plan(self, geoms, canvas=True):
+        """Set the per-image geometry ([n,8] ints, see make_geom) and size the canvas
+        (canvas=False: geometry only, for callers that want the packed output alone)."""
         torch = _torch()
         g = np.ascontiguousarray(np.asarray(geoms, dtype=np.int32).reshape(-1, N.MRX_GEOM_INTS))
         n = g.shape[0]
         if n < 1 or n > self.B:
             raise ValueError(f"batch of {n} images does not fit max_batch={self.B}")
         if self._geom_host is not None and self._geom_host.shape == g.shape and \
-                np.array_equal(self._geom_host, g):
+                np.array_equal(self._geom_host, g) and (self.d_canvas is not None or not canvas):
             return
         if (g[:, :4] < 2).any():
             raise ValueError("image sides must be >= 2")
@@ -117,7 +142,7 @@ class UnmoldEngine:
         off = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(cap, out=off[1:])
         total = int(off[-1])
-        if self.d_canvas is None or self.d_canvas.numel() < total:
+        if canvas and (self.d_canvas is None or self.d_canvas.numel() < total):
             self.d_canvas = None
             self.d_canvas = torch.empty((total,), dtype=torch.uint8, device=self.device)
         self.d_geom[:n].copy_(torch.from_numpy(g))
@@ -125,12 +150,15 @@ class UnmoldEngine:
         self._geom_host = g
         self._offsets = off
         self._n_images = n
+        self._packed_off_host = None
 
     # ------------------------------------------------------------------ launch
-    def enqueue(self, d_detections, d_mrcnn_mask, stream=None):
+    def enqueue(self, d_detections, d_mrcnn_mask, stream=None, expand=True):
         """Enqueue the three kernels for the planned batch on `stream` (no host sync).
         d_detections [n,R,6] and d_mrcnn_mask [n,R,mh,mw,C] are device tensors of the
-        dtypes given at construction."""
+        dtypes given at construction (d_mrcnn_mask may also be PINNED HOST memory: the class
+        gather then reads the wanted elements over PCIe instead of the whole tensor being
+        copied first).  expand=False stops after the class-tile gather."""
         n = self._n_images
         if n == 0:
             raise RuntimeError("call plan() first")
@@ -152,25 +180,94 @@ class UnmoldEngine:
             _ptr(d_detections), _dtype_code(self.det_dtype), n, self.R, self.C, self.mw,
             _ptr(self.d_geom), _ptr(self.d_boxes), _ptr(self.d_class_ids),
             _ptr(self.d_scores), _ptr(self.d_src_index), _ptr(self.d_box_aux),
-            _ptr(self.d_counts), _ptr(self.d_status), _ptr(self.d_job_counter), st),
+            _ptr(self.d_counts), _ptr(self.d_status), _ptr(self.d_sched), st),
             "mrx_unmold_prologue")
         N.check(lib.mrx_gather_tiles(
             _ptr(d_mrcnn_mask), _dtype_code(self.mask_dtype), n, self.R, self.mh, self.mw,
             self.C, _ptr(self.d_class_ids), _ptr(self.d_src_index), _ptr(self.d_counts),
             _ptr(self.d_tiles), st), "mrx_gather_tiles")
-        self.enqueue_expand(stream)
+        if expand:
+            self.enqueue_expand(stream)
 
-    def enqueue_expand(self, stream=None, reset_counter=False):
-        """Only the mask-expand kernel (boxes / tiles / counts already on the device)."""
-        n = self._n_images
-        if reset_counter:
-            self.d_job_counter.zero_()
+    def enqueue_expand(self, stream=None, canvas_ptr=None, images=None):
+        """Only the mask-expand kernel (boxes / tiles / counts already on the device).
+        canvas_ptr: write the canvases at another base address with the planned offsets
+        (an integer device address, e.g. rank 0's receive buffer mapped with mrx_peer_open).
+        images=(b0, b1): only that range of the planned batch (one launch per chunk lets the
+        gather of a finished chunk overlap the next one)."""
+        b0, b1 = (0, self._n_images) if images is None else images
+        if b1 <= b0:
+            return
+        base = _ptr(self.d_canvas) if canvas_ptr is None else C.c_void_p(int(canvas_ptr))
         N.check(self.lib.mrx_mask_expand(
-            _ptr(self.d_tiles), _ptr(self.d_boxes), _ptr(self.d_box_aux), _ptr(self.d_counts),
-            _ptr(self.d_geom),
-            _ptr(self.d_canvas_off), _ptr(self.d_canvas), n, self.R, self.mh, self.mw,
-            self.chunk_bytes, self.ctas_per_sm, _ptr(self.d_job_counter),
+            _ptr(self.d_tiles[b0:]), _ptr(self.d_boxes[b0:]), _ptr(self.d_box_aux[b0:]),
+            _ptr(self.d_counts[b0:]), _ptr(self.d_geom[b0:]),
+            _ptr(self.d_canvas_off[b0:]), base, b1 - b0, self.R, self.mh, self.mw,
+            self.chunk_bytes, self.ctas_per_sm, _ptr(self.d_sched),
             N.stream_ptr(stream)), "mrx_mask_expand")
+
+    def enqueue_expand_values(self, d_values, stream=None):
+        """Parity instrumentation: the same kernel (second instantiation of its template) also
+        stores every pre-threshold sample into d_values (float32, indexed like the canvas)."""
+        n = self._n_images
+        if d_values.dtype != _torch().float32 or d_values.numel() < int(self._offsets[n]):
+            raise ValueError("d_values must be float32 with one element per canvas byte")
+        N.check(self.lib.mrx_mask_expand_values(
+            _ptr(self.d_tiles), _ptr(self.d_boxes), _ptr(self.d_box_aux), _ptr(self.d_counts),
+            _ptr(self.d_geom), _ptr(self.d_canvas_off), _ptr(self.d_canvas), _ptr(d_values),
+            n, self.R, self.mh, self.mw, _ptr(self.d_sched), N.stream_ptr(stream)),
+            "mrx_mask_expand_values")
+
+    # ------------------------------------------------------------------ packed output
+    def packed_layout(self):
+        """(offsets int64 [n+1], total bytes) of the packed output of the planned batch: image b
+        occupies [off[b], off[b+1]) as uint8 [R, H_b, ceil(W_b/8)] (first N_b planes valid)."""
+        n = self._n_images
+        if n == 0:
+            raise RuntimeError("plan() first")
+        if self._packed_off_host is None:
+            g = self._geom_host
+            wb = (g[:, 1].astype(np.int64) + 7) // 8
+            sizes = (g[:, 0].astype(np.int64) * wb * self.R + 15) // 16 * 16
+            off = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(sizes, out=off[1:])
+            self._packed_off_host = off
+            self.d_packed_off = _torch().from_numpy(off[:n].copy()).to(self.device)
+        return self._packed_off_host, int(self._packed_off_host[-1])
+
+    def _packed_buffer(self):
+        torch = _torch()
+        off, total = self.packed_layout()
+        if self.d_packed is None or self.d_packed.numel() < total:
+            self.d_packed = None
+            self.d_packed = torch.empty((total,), dtype=torch.uint8, device=self.device)
+        return off
+
+    def enqueue_expand_packed(self, stream=None, packed_ptr=None, images=None):
+        """EXTENSION (not the reference layout): the expand step writing bit-packed masks
+        directly (mrx_mask_expand_packed): packed[n, y] == np.packbits(masks[y, :, n]).
+        Returns (d_packed, offsets).  packed_ptr: another base address (peer memory);
+        images=(b0, b1): only that range of the planned batch."""
+        b0, b1 = (0, self._n_images) if images is None else images
+        if packed_ptr is None:
+            off = self._packed_buffer()
+            base = _ptr(self.d_packed)
+        else:
+            off, _ = self.packed_layout()
+            base = C.c_void_p(int(packed_ptr))
+        g = self._geom_host
+        if b1 > b0:
+            N.check(self.lib.mrx_mask_expand_packed(
+                _ptr(self.d_tiles[b0:]), _ptr(self.d_boxes[b0:]), _ptr(self.d_counts[b0:]),
+                _ptr(self.d_geom[b0:]), _ptr(self.d_packed_off[b0:]), base, b1 - b0, self.R,
+                self.mh, self.mw, int(g[:, 1].max()), _ptr(self.d_sched), N.stream_ptr(stream)),
+                "mrx_mask_expand_packed")
+        return self.d_packed, off
+
+    def enqueue_packed(self, d_detections, d_mrcnn_mask, stream=None):
+        """prologue -> class-tile gather -> packed expand (no byte canvas is written)."""
+        self.enqueue(d_detections, d_mrcnn_mask, stream, expand=False)
+        return self.enqueue_expand_packed(stream)
 
     # ------------------------------------------------------------------ results
     def canvas_bytes(self, counts):
@@ -186,38 +283,41 @@ class UnmoldEngine:
         return self.d_canvas[o:o + H * W * n_kept].view(H, W, n_kept)
 
     def pack_masks(self, stream=None):
-        """EXTENSION (not the reference layout): bit-pack the canvases of the planned batch on the
-        device.  Returns (d_packed uint8 tensor, offsets int64 array [n+1]); image b occupies
-        d_packed[off[b]:off[b+1]] as [R, H_b, ceil(W_b/8)], the first N_b planes are valid:
-        packed[n, y] == np.packbits(masks[y, :, n])."""
-        torch = _torch()
+        """EXTENSION: bit-pack the byte canvases already written for the planned batch
+        (mrx_pack_masks; same output layout as `enqueue_expand_packed`).  Returns
+        (d_packed, offsets)."""
         n = self._n_images
-        if n == 0:
-            raise RuntimeError("plan() first")
+        off = self._packed_buffer()
         g = self._geom_host
-        wb = (g[:, 1].astype(np.int64) + 7) // 8
-        sizes = g[:, 0].astype(np.int64) * wb * self.R
-        off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(sizes, out=off[1:])
-        total = int(off[-1])
-        if getattr(self, "d_packed", None) is None or self.d_packed.numel() < total:
-            self.d_packed = torch.empty((total,), dtype=torch.uint8, device=self.device)
-        if getattr(self, "_packed_off_host", None) is None or \
-                not np.array_equal(self._packed_off_host, off):
-            self.d_packed_off = torch.from_numpy(off[:n].copy()).to(self.device)
-            self._packed_off_host = off
         N.check(self.lib.mrx_pack_masks(
             _ptr(self.d_canvas), _ptr(self.d_canvas_off), _ptr(self.d_counts), _ptr(self.d_geom),
             _ptr(self.d_packed), _ptr(self.d_packed_off), n, self.R,
             int(g[:, 0].max()), int(g[:, 1].max()), N.stream_ptr(stream)), "mrx_pack_masks")
         return self.d_packed, off
 
-    def fetch_meta(self):
+    def fetch_meta(self, stream=None):
         """Copy counts/status/boxes/class_ids/scores of the planned batch to the host
-        (synchronises the current stream). Raises like numpy would on bad inputs."""
+        (one batch of async copies into cached pinned memory, one synchronisation).
+        Raises like numpy would on bad inputs.  The returned arrays are views of the
+        staging buffers: valid until the next fetch_meta of this engine."""
+        torch = _torch()
         n = self._n_images
-        counts = self.d_counts[:n].cpu().numpy()
-        status = self.d_status[:n].cpu().numpy()
+        if self._h_meta is None:
+            B, R = self.B, self.R
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+            self._h_meta = (pin((B,), torch.int32), pin((B,), torch.int32),
+                            pin((B, R, 4), torch.int32), pin((B, R), torch.int32),
+                            pin((B, R), _torch_dtype(self.det_dtype)))
+        hc, hs, hb, hk, hsc = self._h_meta
+        st = stream or torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st):
+            hc[:n].copy_(self.d_counts[:n], non_blocking=True)
+            hs[:n].copy_(self.d_status[:n], non_blocking=True)
+            hb[:n].copy_(self.d_boxes[:n], non_blocking=True)
+            hk[:n].copy_(self.d_class_ids[:n], non_blocking=True)
+            hsc[:n].copy_(self.d_scores[:n], non_blocking=True)
+        st.synchronize()
+        counts, status = hc[:n].numpy(), hs[:n].numpy()
         if (status & N.MRX_ST_CLASS_RANGE).any():
             b = int(np.nonzero(status & N.MRX_ST_CLASS_RANGE)[0][0])
             raise IndexError(f"image {b}: class id out of bounds for axis 3 with size {self.C}")
@@ -225,10 +325,7 @@ class UnmoldEngine:
             b = int(np.nonzero(status & N.MRX_ST_BOX_RANGE)[0][0])
             raise ValueError(f"image {b}: a detection box falls outside the original image; "
                              "the reference's mask paste cannot broadcast it")
-        boxes = self.d_boxes[:n].cpu().numpy()
-        class_ids = self.d_class_ids[:n].cpu().numpy()
-        scores = self.d_scores[:n].cpu().numpy()
-        return counts, boxes, class_ids, scores
+        return counts, hb[:n].numpy(), hk[:n].numpy(), hsc[:n].numpy()
 
 
 class AnchorGenerator:
@@ -363,6 +460,52 @@ class Molder:
         return out, u8, window, scale, padding
 
 
+    # ------------------------------------------------------------------ batched (one launch each)
+    def cv2_resize_batch_device(self, images, size_hw, stream=None):
+        """`cv2.resize(img, (S, S))` for a list of uint8 HxWx3 NumPy images of ANY sizes in one
+        launch: one pinned staging buffer, one H2D copy.  Returns uint8 [B, dh, dw, 3] on the
+        device."""
+        torch = _torch()
+        B = len(images)
+        dh, dw = int(size_hw[0]), int(size_hw[1])
+        sizes = [int(im.shape[0]) * int(im.shape[1]) * 3 for im in images]
+        off = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum((np.asarray(sizes, dtype=np.int64) + 15) // 16 * 16, out=off[1:])
+        total = int(off[-1])
+        if getattr(self, "_h_stage", None) is None or self._h_stage.numel() < total:
+            self._h_stage = torch.empty((total,), dtype=torch.uint8).pin_memory()
+        hs = self._h_stage.numpy()
+        hw = np.empty((B, 2), dtype=np.int32)
+        for b, im in enumerate(images):
+            hs[int(off[b]):int(off[b]) + sizes[b]] = np.ascontiguousarray(im).reshape(-1)
+            hw[b] = im.shape[:2]
+        d_src = self._h_stage[:total].to(self.device, non_blocking=True)
+        d_off = torch.from_numpy(off[:B].copy()).to(self.device)
+        d_hw = torch.from_numpy(hw).to(self.device)
+        out = torch.empty((B, dh, dw, 3), dtype=torch.uint8, device=self.device)
+        N.check(self.lib.mrx_cv2_resize_u8c3_batch(
+            _ptr(d_src), _ptr(d_off), _ptr(d_hw), _ptr(out), B, dh, dw, N.stream_ptr(stream)),
+            "mrx_cv2_resize_u8c3_batch")
+        return out
+
+    def mold_batch_device(self, d_imgs, out_dtype=np.float32, stream=None):
+        """resize_image + mold_image for uint8 [B,h,w,3] device images of one size, one launch.
+        Returns (molded [B,oh,ow,3], window, scale, padding)."""
+        torch = _torch()
+        cfg = self.config
+        B, h, w = int(d_imgs.shape[0]), int(d_imgs.shape[1]), int(d_imgs.shape[2])
+        nh, nw, top, left, oh, ow, window, scale, padding = resize_image_geometry(
+            h, w, cfg.IMAGE_MIN_DIM, cfg.IMAGE_MAX_DIM, cfg.IMAGE_MIN_SCALE,
+            cfg.IMAGE_RESIZE_MODE)
+        out = torch.empty((B, oh, ow, 3), dtype=_torch_dtype(out_dtype), device=self.device)
+        mean = [float(v) for v in np.asarray(cfg.MEAN_PIXEL, dtype=np.float64)]
+        N.check(self.lib.mrx_mold_image_batch(
+            _ptr(d_imgs), B, h, w, nh, nw, top, left, oh, ow, N.double_array(mean),
+            _dtype_code(out_dtype), _ptr(out), C.c_void_p(0), N.stream_ptr(stream)),
+            "mrx_mold_image_batch")
+        return out, window, scale, padding
+
+
 class StreamingUnmolder:
     """Host-buffer pipeline around UnmoldEngine for a stream of equally-shaped batches:
     the H2D copy of batch k+1 (own stream, double-buffered device inputs) overlaps the D2H
@@ -373,20 +516,36 @@ class StreamingUnmolder:
         for k, (h_det, h_msk) in enumerate(batches):      # pinned [n,R,6] / [n,R,mh,mw,C]
             sm.submit(h_det, h_msk)
             if k: counts, boxes, masks = sm.wait(k - 1)
-    """
 
-    def __init__(self, engine, geoms):
+    packed=True (EXTENSION, not the reference layout): the expand kernel writes bit-packed masks
+    (`mrx_mask_expand_packed`) and only those travel back: 8x fewer D2H bytes; the host buffer
+    then holds, per image, uint8 [R, H, ceil(W/8)] at `engine.packed_layout()` offsets.
+
+    mask_upload="zero_copy": `mrcnn_mask` is not copied to the device at all -- the class-tile
+    gather kernel reads the 1/C of it that is needed straight from the pinned host buffer over
+    PCIe (detections are still copied: 2.4 KB per image)."""
+
+    def __init__(self, engine, geoms, packed=False, mask_upload="copy"):
         torch = _torch()
+        if mask_upload not in ("copy", "zero_copy"):
+            raise ValueError("mask_upload: 'copy' or 'zero_copy'")
         self.eng = engine
-        engine.plan(geoms)
+        self.packed = bool(packed)
+        self.zero_copy = mask_upload == "zero_copy"
+        engine.plan(geoms, canvas=not self.packed)
         n = engine._n_images
         self.n = n
         dev = engine.device
         det_t, msk_t = _torch_dtype(engine.det_dtype), _torch_dtype(engine.mask_dtype)
         self.d_det = [torch.empty((n, engine.R, 6), dtype=det_t, device=dev) for _ in range(2)]
-        self.d_msk = [torch.empty((n, engine.R, engine.mh, engine.mw, engine.C), dtype=msk_t,
-                                  device=dev) for _ in range(2)]
-        self.total = int(engine._offsets[n])
+        self.d_msk = None if self.zero_copy else [
+            torch.empty((n, engine.R, engine.mh, engine.mw, engine.C), dtype=msk_t, device=dev)
+            for _ in range(2)]
+        if self.packed:
+            self.total = engine.packed_layout()[1]
+            engine._packed_buffer()
+        else:
+            self.total = int(engine._offsets[n])
         self.h_out = [torch.empty((self.total,), dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.h_counts = [torch.empty((n,), dtype=torch.int32).pin_memory() for _ in range(2)]
         self.h_boxes = [torch.empty((n, engine.R, 4), dtype=torch.int32).pin_memory()
@@ -397,8 +556,11 @@ class StreamingUnmolder:
         self.in_free = [torch.cuda.Event() for _ in range(2)]
         self.out_done = {}
         self.k = 0
+        msk_bytes = n * engine.R * engine.mh * engine.mw * engine.C * engine.mask_dtype.itemsize
         self.h2d_bytes = self.d_det[0].numel() * self.d_det[0].element_size() + \
-            self.d_msk[0].numel() * self.d_msk[0].element_size()
+            (0 if self.zero_copy else msk_bytes)
+        # zero copy: the gather kernel pulls one 32-byte sector per wanted element over PCIe
+        self.pcie_read_bytes = n * engine.R * engine.mh * engine.mw * 32 if self.zero_copy else 0
         self.d2h_bytes = self.total + 4 * (n + 4 * n * engine.R)
 
     def submit(self, h_det, h_msk):
@@ -408,15 +570,25 @@ class StreamingUnmolder:
             if k >= 2:
                 self.copy_stream.wait_event(self.in_free[i])     # kernels of batch k-2 read d_*[i]
             self.d_det[i].copy_(h_det, non_blocking=True)
-            self.d_msk[i].copy_(h_msk, non_blocking=True)
+            if not self.zero_copy:
+                self.d_msk[i].copy_(h_msk, non_blocking=True)
             self.h2d_done[i].record(self.copy_stream)
         ms = self.main_stream
         ms.wait_event(self.h2d_done[i])
-        self.eng.enqueue(self.d_det[i], self.d_msk[i], ms)       # also orders after batch k-1's D2H
+        msk = h_msk if self.zero_copy else self.d_msk[i]
+        if self.zero_copy and not h_msk.is_pinned():
+            raise ValueError("zero_copy needs the mask tensor in pinned host memory")
+        # (also orders after batch k-1's D2H, which reads the output buffer this batch rewrites)
+        if self.packed:
+            self.eng.enqueue_packed(self.d_det[i], msk, ms)
+            d_out = self.eng.d_packed
+        else:
+            self.eng.enqueue(self.d_det[i], msk, ms)
+            d_out = self.eng.d_canvas
         self.in_free[i].record(ms)
         self.h_counts[i].copy_(self.eng.d_counts[:self.n], non_blocking=True)
         self.h_boxes[i].copy_(self.eng.d_boxes[:self.n], non_blocking=True)
-        self.h_out[i].copy_(self.eng.d_canvas[:self.total], non_blocking=True)
+        self.h_out[i].copy_(d_out[:self.total], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(ms)
         self.out_done[k] = ev
@@ -425,7 +597,7 @@ class StreamingUnmolder:
 
     def wait(self, k):
         """Block until batch k's results are in pinned host memory; returns
-        (counts [n] int32, boxes [n,R,4] int32, canvas bytes uint8) as torch CPU tensors."""
+        (counts [n] int32, boxes [n,R,4] int32, output bytes uint8) as torch CPU tensors."""
         self.out_done.pop(k).synchronize()
         i = k % 2
         return self.h_counts[i], self.h_boxes[i], self.h_out[i]

@@ -107,9 +107,16 @@ def tensor_proto_to_ndarray(tensor, dtype=None):
             packed.append((np.dtype("<f8"), v[0], v[1]))
         elif num == 6 and wt == 1:
             singles.append((np.dtype("<f8"), v[0], v[1]))
+    for d, lo, hi in packed + singles:
+        if (hi - lo) % d.itemsize:
+            raise ValueError(f"TensorProto value field of {hi - lo} bytes is not a whole number "
+                             f"of {d.itemsize}-byte elements")
     if content is not None and content[1] > content[0]:
         if dt not in _NP_OF_DT:
             raise ValueError(f"tensor_content with unsupported dtype enum {dt}")
+        if (content[1] - content[0]) % _NP_OF_DT[dt].itemsize:
+            raise ValueError(f"tensor_content of {content[1] - content[0]} bytes is not a whole "
+                             f"number of {_NP_OF_DT[dt].itemsize}-byte elements")
         arr = np.frombuffer(buf, dtype=_NP_OF_DT[dt], count=(content[1] - content[0]) // _NP_OF_DT[dt].itemsize,
                             offset=content[0])
     elif len(packed) == 1 and not singles:
@@ -122,8 +129,17 @@ def tensor_proto_to_ndarray(tensor, dtype=None):
                               for _, lo, hi in runs])
     else:
         arr = np.empty((0,), dtype=_NP_OF_DT.get(dt, np.dtype("<f4")))
-    if shape and all(s >= 0 for s in shape) and int(np.prod(shape)) == arr.size:
-        arr = arr.reshape(shape)
+    if shape and all(s >= 0 for s in shape):
+        if int(np.prod(shape)) != arr.size:
+            # TensorFlow allows a single repeated value to stand for a whole tensor; anything
+            # else is a malformed message
+            if arr.size == 1:
+                arr = np.full(shape, arr.reshape(-1)[0], dtype=arr.dtype)
+            else:
+                raise ValueError(f"tensor_shape {list(shape)} does not match the {arr.size} "
+                                 "values of the message")
+        else:
+            arr = arr.reshape(shape)
     if dtype is not None and arr.dtype != np.dtype(dtype):
         arr = arr.astype(dtype)
     return arr
@@ -145,6 +161,10 @@ def decode_predict_outputs(detection_tensor, mask_tensor, det_shape, mask_shape,
 
 
 def _put_varint(out, v):
+    v = int(v)
+    if v < 0:
+        # protobuf encodes negative int64 as the 10-byte two's complement varint
+        v &= (1 << 64) - 1
     while True:
         b = v & 0x7F
         v >>= 7
@@ -164,6 +184,8 @@ def ndarray_to_tensor_proto_bytes(arr, shape=None):
     if arr.dtype not in _DT_OF_NP:
         raise ValueError(f"unsupported dtype {arr.dtype}")
     dims = list(arr.shape if shape is None else shape)
+    if any(int(d) < 0 for d in dims):
+        raise ValueError(f"negative dimension in shape {dims} (a request tensor is fully shaped)")
     if int(np.prod(dims)) != arr.size:
         raise ValueError("shape does not match the number of elements")
     shape_msg = bytearray()

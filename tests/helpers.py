@@ -43,3 +43,53 @@ def compare_masks(gpu_masks, ref_masks, resized, boxes):
     for r in resized:
         in_band += int((np.abs(r - 0.5) <= MASK_VALUE_ATOL).sum())
     return bad, in_band
+
+
+def mask_parity_stats(gpu_masks, ref_masks, resized, boxes):
+    """Everything the parity contract talks about, for one image: number of mask pixels that
+    differ from the oracle outside / inside the +-MASK_VALUE_ATOL band around the threshold,
+    number of in-box pixels inside the band, number of pixels compared."""
+    assert gpu_masks.shape == ref_masks.shape, (gpu_masks.shape, ref_masks.shape)
+    diff = gpu_masks != ref_masks
+    flips_out = flips_in = band = 0
+    outside = diff.copy()
+    for i, (y1, x1, y2, x2) in enumerate(boxes):
+        near = np.abs(resized[i] - 0.5) <= MASK_VALUE_ATOL
+        band += int(near.sum())
+        d = diff[y1:y2, x1:x2, i]
+        if d.any():
+            flips_out += int((d & ~near).sum())
+            flips_in += int((d & near).sum())
+        outside[y1:y2, x1:x2, i] = False
+    flips_out += int(outside.sum())          # a set pixel outside its box is always an error
+    return {"flips_outside_band": flips_out, "flips_inside_band": flips_in,
+            "band_pixels": band, "pixels": int(gpu_masks.size)}
+
+
+def value_parity_stats(values, resized, boxes):
+    """values: float32 [H,W,N] pre-threshold samples the production kernel stored (only in-box
+    elements are meaningful).  Returns max |gpu - oracle| over every in-box sample and the
+    sample count."""
+    worst, count = 0.0, 0
+    for i, (y1, x1, y2, x2) in enumerate(boxes):
+        v = values[y1:y2, x1:x2, i].astype(np.float64)
+        err = np.abs(v - resized[i])
+        if err.size:
+            worst = max(worst, float(err.max()))
+            count += err.size
+    return {"max_abs_err": worst, "samples": count}
+
+
+def record_stats(name, stats):
+    """Append one line to gpurun_out/parity_stats.jsonl (copied to profiles/ by hand)."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_stats.jsonl"), "a") as f:
+            f.write(json.dumps({"case": name, **stats}) + "\n")
+    except OSError:
+        pass

@@ -121,7 +121,7 @@ def test_do_inference_flow_lists_and_wire_bytes(cuda_device):
     try:
         for fn in (predict_lists, predict_wire):
             serve.set_predict_fn(fn)
-            b, c, s, m = serve.do_inference(img)
+            b, c, s, m = serve.do_inference_unmolded(img)
             assert np.array_equal(b, ref[0]) and np.array_equal(c, ref[1])
             assert np.array_equal(s, ref[2]) and s.dtype == ref[2].dtype
             assert m.shape == ref[3].shape and m.dtype == np.bool_
@@ -129,3 +129,113 @@ def test_do_inference_flow_lists_and_wire_bytes(cuda_device):
         assert seen["dtypes"] == (np.float32, np.float32, np.float32)    # serve.py:117-119
     finally:
         serve.set_predict_fn(None)
+
+
+def _fake_model(rng, imgs, n_inst):
+    """Synthetic TF-Serving: per request image, detections + masks laid out for the molded
+    geometry `preprocess_input` produces (looked up by the molded tensor's id in call order)."""
+    from matterport_maskrcnn_with_tensorflow_serving_b200 import configs as cf
+
+    outs = []
+    for img in imgs:
+        molded, meta, anchors, window = serve.preprocess_input(img, cf.IMAGE_SIZE, np.float32)
+        im = synth.make_image(rng, img.shape[:2], n_inst, num_classes=cf.OUT_MASK_SHAPE[-1],
+                              max_instances=cf.OUT_DETECTION_SHAPE[0],
+                              mold=(molded.shape, window))
+        outs.append((im, molded, meta, window))
+    calls = {"k": 0, "inputs": []}
+
+    def predict(molded_f32, meta_f32, anchors_f32):
+        k = calls["k"]
+        calls["k"] += 1
+        calls["inputs"].append((molded_f32, meta_f32))
+        im = outs[k % len(outs)][0]
+        return im.detections.reshape(-1).tolist(), im.mrcnn_mask.reshape(-1).tolist()
+
+    return outs, predict, calls
+
+
+def test_do_inference_returns_the_saved_overlay_path(cuda_device, tmp_path):
+    """serve.py:141-173: `do_inference(img)` returns `save_path` of media/mask-<uuid>.png whose
+    pixels are the mask overlay of display_instances (oracle.composite_instances of the
+    oracle's unmold), computed without the masks leaving the device."""
+    import random
+
+    import cv2
+
+    from matterport_maskrcnn_with_tensorflow_serving_b200 import visualize
+
+    rng = np.random.default_rng(19)
+    img = synth.synth_rgb_image(rng, 300, 420)
+    outs, predict, calls = _fake_model(rng, [img], 23)
+    im, molded, meta, window = outs[0]
+    rb, rc, rs, rm = oracle.unmold_detections(
+        im.detections.astype(np.float64), im.mrcnn_mask.astype(np.float64), img.shape,
+        molded.shape, window)
+    colors = visualize.random_colors(100, rng=random.Random(5))
+    ref = oracle.composite_instances(img, rb, rm, colors)
+    serve.set_predict_fn(predict)
+    try:
+        path = serve.do_inference(img, colors=colors, media_dir=str(tmp_path))
+    finally:
+        serve.set_predict_fn(None)
+    assert isinstance(path, str) and path.startswith(str(tmp_path))
+    name = path[len(str(tmp_path)) + 1:]
+    assert name.startswith("mask-") and name.endswith(".png") and len(name) == len("mask-.png") + 36
+    got = cv2.cvtColor(cv2.imread(path, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+def test_do_inference_batch_matches_single_calls(cuda_device, tmp_path):
+    """Batched surface: images of different sizes through
+    `do_inference_batch` give, per image, exactly the picture `do_inference` gives alone; the
+    batched pre-processing sends the RPC the same tensors the single path sends."""
+    import random
+
+    import cv2
+
+    from matterport_maskrcnn_with_tensorflow_serving_b200 import visualize
+
+    rng = np.random.default_rng(29)
+    imgs = [synth.synth_rgb_image(rng, 300, 420), synth.synth_rgb_image(rng, 640, 640),
+            synth.synth_rgb_image(rng, 222, 150)]
+    outs, predict, calls = _fake_model(rng, imgs, 11)
+    colors = visualize.random_colors(100, rng=random.Random(6))
+    serve.set_predict_fn(predict)
+    try:
+        calls["k"] = 0
+        calls["inputs"].clear()
+        singles = [serve.do_inference(img, colors=colors, media_dir=str(tmp_path)) for img in imgs]
+        single_inputs = list(calls["inputs"])
+        calls["k"] = 0
+        calls["inputs"].clear()
+        paths = serve.do_inference_batch(imgs, colors=colors, media_dir=str(tmp_path))
+        batch_inputs = list(calls["inputs"])
+    finally:
+        serve.set_predict_fn(None)
+    assert len(paths) == len(imgs) and len(set(paths + singles)) == 2 * len(imgs)
+    for a, b in zip(singles, paths):
+        assert np.array_equal(cv2.imread(a), cv2.imread(b))
+    for (m1, meta1), (m2, meta2) in zip(single_inputs, batch_inputs):
+        assert m1.dtype == m2.dtype == np.float32 and np.array_equal(m1, m2)
+        assert np.array_equal(meta1, meta2)
+
+
+@pytest.mark.parametrize("img_size", [640, None])
+def test_preprocess_input_batch_matches_oracle(cuda_device, img_size):
+    """One cv2.resize launch + one mold launch for the batch == the oracle per image."""
+    rng = np.random.default_rng(31)
+    if img_size is None:
+        imgs = [synth.synth_rgb_image(rng, 480, 640) for _ in range(3)]
+    else:
+        imgs = [synth.synth_rgb_image(rng, 480, 640), synth.synth_rgb_image(rng, 1280, 1280),
+                synth.synth_rgb_image(rng, 97, 333), synth.synth_rgb_image(rng, 640, 640)]
+    molded, metas, anchors, windows = serve.preprocess_input_batch(imgs, img_size, np.float64)
+    for b, img in enumerate(imgs):
+        ref_molded, ref_meta, ref_anchors, ref_window = oracle.preprocess_input(img, img_size)
+        assert windows[b] == ref_window
+        assert molded[b].dtype == ref_molded.dtype and np.array_equal(molded[b], ref_molded)
+        assert np.array_equal(metas[b], ref_meta)
+        assert np.array_equal(anchors.view(np.uint32), ref_anchors.view(np.uint32))
+    m32, _, _, _ = serve.preprocess_input_batch(imgs, img_size)      # wire dtype by default
+    assert m32.dtype == np.float32 and np.array_equal(m32, molded.astype(np.float32))

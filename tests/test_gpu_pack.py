@@ -10,13 +10,19 @@ from helpers import item_of
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("direct", [True, False], ids=["expand_packed", "pack_kernel"])
 @pytest.mark.parametrize("hw,n,R", [((96, 128), 12, 16), ((75, 333), 37, 40), ((64, 21), 5, 8),
                                     ((40, 260), 0, 4), ((300, 517), 100, 100),
-                                    ((1024, 1024), 100, 100)])
-def test_packed_masks_equal_packbits(cuda_device, hw, n, R):
+                                    ((1024, 1024), 100, 100), ((800, 1333), 61, 100),
+                                    ((33, 1000), 7, 8), ((17, 9), 3, 4)])
+def test_packed_masks_equal_packbits(cuda_device, hw, n, R, direct):
+    """Both producers of the packed layout -- the expand kernel that writes bits directly
+    (mrx_mask_expand_packed) and the pack kernel over a byte canvas (mrx_pack_masks) -- must give
+    exactly np.packbits of the bool masks `unmold_detections` returns."""
     im = synth.make_batch(61, 1, hw, n, num_classes=4, max_instances=R)[0]
     b, c, s, m = api_utils.unmold_detections(*item_of(im, np.float32))
-    (pb, pc, ps, packed), = api_utils.unmold_detections_packed_batch([item_of(im, np.float32)])
+    (pb, pc, ps, packed), = api_utils.unmold_detections_packed_batch([item_of(im, np.float32)],
+                                                                     direct=direct)
     assert np.array_equal(pb, b) and np.array_equal(pc, c) and np.array_equal(ps, s)
     H, W = hw
     assert packed.dtype == np.uint8 and packed.shape == (b.shape[0], H, (W + 7) // 8)
@@ -27,10 +33,55 @@ def test_packed_masks_equal_packbits(cuda_device, hw, n, R):
     assert restored.shape == m.shape and np.array_equal(restored, m)
 
 
-def test_packed_batch_ragged(cuda_device):
+@pytest.mark.parametrize("direct", [True, False], ids=["expand_packed", "pack_kernel"])
+def test_packed_batch_ragged(cuda_device, direct):
     ims = synth.make_batch(62, 3, (120, 200), (0, 20), num_classes=3, max_instances=20)
-    res = api_utils.unmold_detections_packed_batch([item_of(im, np.float32) for im in ims])
+    res = api_utils.unmold_detections_packed_batch([item_of(im, np.float32) for im in ims],
+                                                   direct=direct)
     for (b, c, s, packed), im in zip(res, ims):
         rb, rc, rs, rm = api_utils.unmold_detections(*item_of(im, np.float32))
         assert np.array_equal(b, rb)
         assert np.array_equal(api_utils.unpack_masks(packed, 200), rm)
+
+
+@pytest.mark.parametrize("hw,n,R,batch", [((1024, 1024), 100, 100, 3), ((2160, 3840), 50, 50, 1),
+                                          ((800, 1333), (1, 100), 100, 4),
+                                          ((96, 160), (0, 16), 16, 9)])
+def test_expand_packed_equals_byte_canvas_on_device(cuda_device, hw, n, R, batch):
+    """Full-size shapes (BASELINE.json configs[1], [2], [3]): the directly packed output equals
+    the bit-packing of the byte canvas the headline kernel writes, plane for plane, compared on
+    the device (no oracle in the loop: two independent kernels, one arithmetic)."""
+    import torch
+
+    from matterport_maskrcnn_with_tensorflow_serving_b200.engine import UnmoldEngine, make_geom
+
+    ims = synth.make_batch(63, batch, hw, n, num_classes=5, max_instances=R)
+    eng = UnmoldEngine(batch, R, (28, 28), 5)
+    eng.plan([make_geom(im.original_image_shape, im.image_shape, im.window) for im in ims])
+    d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
+    d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
+    eng.enqueue(d_det, d_msk)
+    d_packed, off = eng.enqueue_expand_packed()
+    direct = d_packed[:int(off[-1])].clone()
+    d_packed.fill_(0xAA)
+    d_packed2, off2 = eng.pack_masks()
+    counts, boxes, cls, scores = eng.fetch_meta()
+    H, W = hw
+    wb = (W + 7) // 8
+    weights = (2 ** torch.arange(7, -1, -1, device="cuda")).to(torch.int32)
+    for b in range(batch):
+        k = int(counts[b])
+        if k == 0:
+            continue
+        lo = int(off[b])
+        a = direct[lo:lo + k * H * wb]
+        c = d_packed2[lo:lo + k * H * wb]
+        assert torch.equal(a, c), f"image {b}: direct and pack kernel differ"
+        # and both equal packbits of the canvas, computed with torch on the device for one plane
+        i = k // 2
+        plane = eng.canvas_view(b, k)[:, :, i].to(torch.int32)
+        pad = wb * 8 - W
+        if pad:
+            plane = torch.nn.functional.pad(plane, (0, pad))
+        ref = (plane.view(H, wb, 8) * weights).sum(-1).to(torch.uint8)
+        assert torch.equal(a.view(k, H, wb)[i], ref)

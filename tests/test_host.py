@@ -42,7 +42,13 @@ def test_host_side_argument_validation():
     assert lib.mrx_anchors(None, 1024, 1024, None, None, strides, 5, 3, 1, None) == -1
     assert lib.mrx_mask_expand(None, None, None, None, None, None, None, 1, 100, 28, 28, 0, 0,
                                None, None) == -1
-    assert lib.mrx_resize_tile_f32(C.c_void_p(16), 28, 30, 4, 4, C.c_void_p(16), None) == -2  # mw % 4
+    assert lib.mrx_mask_expand_values(None, None, None, None, None, None, None, None, 1, 100, 28,
+                                      28, None, None) == -1
+    p16 = C.c_void_p(16)
+    assert lib.mrx_mask_expand_packed(p16, p16, p16, p16, p16, p16, 1, 100, 28, 32, 1024, p16,
+                                      None) == -2      # mask tiles wider than 30 columns
+    assert b"30" in lib.mrx_last_error()
+    assert lib.mrx_peer_export(None, None) == -1 and lib.mrx_peer_wait(None, 1, 1, None) == -1
 
 
 def test_product_path_has_no_cpu_fallback():
@@ -122,6 +128,17 @@ def test_partition_images_contiguous_and_balanced():
                                                [(0, 4), (4, 7), (7, 10)])
 
 
+def test_chunk_splits():
+    assert sharding.chunk_bounds(16, 4) == [(0, 4), (4, 8), (8, 12), (12, 16)]
+    assert sharding.chunk_bounds(3, 8) == [(0, 1), (1, 2), (2, 3)]
+    assert sharding.chunk_bounds(0, 4) == []
+    for size, n in [(1000, 4), (17, 4), (0, 3), (3355443200, 7), (16, 1)]:
+        r = sharding.RootGather.chunk_ranges(size, n)
+        assert len(r) == n and r[0][0] == 0 and r[-1][1] == size
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(lo % 16 == 0 for lo, _ in r)
+
+
 _GLOO_WORKER = r'''
 import os, sys
 import numpy as np, torch, torch.distributed as dist
@@ -137,13 +154,36 @@ local = torch.cat([torch.full((costs[i],), 10 * i + 1, dtype=torch.uint8) for i 
     if hi > lo else torch.empty(0, dtype=torch.uint8)
 sizes = [sum(costs[a:b]) for a, b in parts]
 out = sharding.gather_bytes_to_root(local, sizes, 0)
+want = np.concatenate([np.full(costs[i], 10 * i + 1, np.uint8) for i in range(len(costs))])
 if rank == 0:
     got = torch.cat(out).numpy()
-    want = np.concatenate([np.full(costs[i], 10 * i + 1, np.uint8) for i in range(len(costs))])
     assert np.array_equal(got, want), (got, want)
     print("GATHER_OK", parts)
 else:
     assert out is None
+# pipelined gather into one preallocated buffer, several chunks per rank, used twice
+big = [4000 + 37, 2500 + 3]
+src = [torch.arange(big[r], dtype=torch.int64).mul(7 + r).remainder(251).to(torch.uint8) for r in range(2)]
+g = sharding.RootGather(big, "cpu")
+for rep in range(2):
+    mine = (src[rank] + rep).to(torch.uint8)
+    n_chunks = 3
+    g.begin(n_chunks)
+    if rank == 0:
+        g.slot(0).copy_(mine)                 # rank 0's kernels write straight into its slot
+        for _ in range(n_chunks):
+            g.post()
+    else:
+        for lo, hi in sharding.RootGather.chunk_ranges(big[rank], n_chunks):
+            g.post(mine, lo, hi)
+    g.wait()
+    if rank == 0:
+        for r in range(2):
+            assert torch.equal(g.slot(r), (src[r] + rep).to(torch.uint8)), (rep, r)
+        assert g.recv.numel() == sum(big)
+    dist.barrier()
+if rank == 0:
+    print("PIPELINED_OK")
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -158,7 +198,7 @@ def test_gather_to_root_gloo_world_size_2(tmp_path):
              for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
-    assert "GATHER_OK" in outs[0]
+    assert "GATHER_OK" in outs[0] and "PIPELINED_OK" in outs[0]
 
 
 def test_dropin_shims_resolve_the_reference_imports():

@@ -51,13 +51,11 @@ def unmold_case(name, batch, hw, n, classes, R, iters, base_images=4, seed=7, co
     algo = out_bytes + masks * (28 * 28 * 4 + 24)
     step_ms, _ = time_ms(lambda: eng.enqueue(d_det, d_msk), iters)
 
-    def expand_only():
-        eng.d_job_counter.zero_()
-        eng.enqueue_expand()
-    # the counter reset is a separate tiny launch; time the pair, then the reset alone
-    both_ms, _ = time_ms(expand_only, iters)
-    reset_ms, _ = time_ms(lambda: eng.d_job_counter.zero_(), iters)
-    k_ms = both_ms - reset_ms
+    k_ms, _ = time_ms(lambda: eng.enqueue_expand(), iters)
+    # extension layout: the expand kernel that writes bit-packed masks, and the pack kernel
+    pk_ms, _ = time_ms(lambda: eng.enqueue_expand_packed(), iters)
+    pack_ms, _ = time_ms(lambda: eng.pack_masks(), iters)
+    pro_ms, _ = time_ms(lambda: eng.enqueue(d_det, d_msk, expand=False), iters)
     if composite:
         import random
 
@@ -76,7 +74,12 @@ def unmold_case(name, batch, hw, n, classes, R, iters, base_images=4, seed=7, co
                       "canvas_GB": round(out_bytes / 1e9, 3), "step_ms": round(step_ms, 4),
                       "Mmasks_per_s": round(masks / step_ms / 1e3, 3),
                       "expand_ms": round(k_ms, 4),
-                      "expand_algorithmic_GBps": round(algo / k_ms / 1e6, 1)}), flush=True)
+                      "expand_algorithmic_GBps": round(algo / k_ms / 1e6, 1),
+                      "prologue_plus_class_gather_ms": round(pro_ms, 4),
+                      "expand_packed_ms": round(pk_ms, 4),
+                      "expand_packed_Mmasks_per_s": round(masks / pk_ms / 1e3, 2),
+                      "pack_kernel_ms": round(pack_ms, 4),
+                      "pack_kernel_canvas_read_GBps": round(out_bytes / pack_ms / 1e6, 1)}), flush=True)
     del eng, d_det, d_msk
     torch.cuda.empty_cache()
 

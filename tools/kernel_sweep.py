@@ -1,0 +1,87 @@
+"""Developer sweep: time the expand kernels on BASELINE configs[1] for several compiled
+variants of the team kernel.  Needs the development build of the library:
+
+    MRX_NVCC_FLAGS=-DMRX_DEV MRX_LIB_NAME=libmrx_dev.so python -m matterport_maskrcnn_with_tensorflow_serving_b200.build
+    MRX_LIB=libmrx_dev.so python tools/kernel_sweep.py --variants 6x5x10w0 6x5x10w1 ...
+
+Each variant runs in its own subprocess (the library reads MRX_EXPAND_TEAMS / MRX_EXPAND_FLAGS
+at launch time in -DMRX_DEV builds only).  Not the contract bench (see bench.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def child(args):
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from matterport_maskrcnn_with_tensorflow_serving_b200.engine import UnmoldEngine, make_geom
+
+    torch.cuda.set_device(0)
+    ims = bench.make_bench_images(0, args.batch)
+    d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
+    d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
+    eng = UnmoldEngine(args.batch, 100, (28, 28), 81)
+    eng.plan([make_geom(im.original_image_shape, im.image_shape, im.window) for im in ims])
+    for _ in range(3):
+        eng.enqueue(d_det, d_msk)
+    torch.cuda.synchronize()
+    counts = eng.d_counts[:args.batch].cpu().numpy()
+    nbytes = eng.canvas_bytes(counts) + int(counts.sum()) * 3160
+    digest = int(eng.d_canvas[:int(eng._offsets[args.batch])].to(torch.int64).sum().item())
+
+    def timeit(fn):
+        ts = []
+        for _ in range(args.iters):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2], ts[0]
+
+    exp_med, exp_min = timeit(lambda: eng.enqueue_expand())
+    step_med, _ = timeit(lambda: eng.enqueue(d_det, d_msk))
+    pre_med, _ = timeit(lambda: eng.enqueue(d_det, d_msk, expand=False))
+    pk_med, pk_min = timeit(lambda: eng.enqueue_expand_packed())
+    pack_med, _ = timeit(lambda: eng.pack_masks())
+    print(json.dumps({"variant": os.environ.get("MRX_EXPAND_TEAMS", "default"),
+                      "flags": os.environ.get("MRX_EXPAND_FLAGS", ""),
+                      "expand_ms": round(exp_med, 4), "expand_ms_min": round(exp_min, 4),
+                      "expand_GBps": round(nbytes / exp_med / 1e6, 1), "step_ms": round(step_med, 4),
+                      "prologue_gather_ms": round(pre_med, 4),
+                      "expand_packed_ms": round(pk_med, 4), "expand_packed_ms_min": round(pk_min, 4),
+                      "pack_kernel_ms": round(pack_med, 4), "ones": digest}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--variants", nargs="*", default=["6x5x10w0", "6x5x10w1"])
+    ap.add_argument("--flags", nargs="*", default=[""])
+    ap.add_argument("--child", action="store_true")
+    args = ap.parse_args()
+    if args.child:
+        return child(args)
+    for v in args.variants:
+        for f in args.flags:
+            env = dict(os.environ, MRX_EXPAND_TEAMS=v)
+            if f:
+                env["MRX_EXPAND_FLAGS"] = f
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--batch",
+                            str(args.batch), "--iters", str(args.iters)], env=env, check=False)
+
+
+if __name__ == "__main__":
+    main()
