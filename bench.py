@@ -4,7 +4,7 @@
     python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun)
     python bench.py --impl reference ...                   (the reference's CPU algorithm)
 
-A step = one pass of the hot path (prologue -> class-tile gather -> fused mask expand)
+A step = one pass of the hot path (prologue + class-tile gather, one launch -> fused mask expand)
 over one batch of synthetic detections: BASELINE.json configs[1], 32 distinct images of
 1024x1024 with 100 instances each, per GPU (weak scaling: every rank processes its own batch;
 the path has no exchange step, the final gather to rank 0 is timed separately as `gather`).
@@ -533,16 +533,14 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ev0.record(stream)
     for s in range(args.steps):
-        N.check(lib.mrx_unmold_prologue(P(d_det), N.MRX_F32, BATCH, N_INST, CLASSES, 28,
-                                        P(eng.d_geom), P(eng.d_boxes), P(eng.d_class_ids),
-                                        P(eng.d_scores), P(eng.d_src_index), P(eng.d_box_aux),
-                                        P(eng.d_counts), P(eng.d_status), P(eng.d_sched),
-                                        st), "prologue")
-        N.check(lib.mrx_gather_tiles(P(d_msk), N.MRX_F32, BATCH, N_INST, 28, 28, CLASSES,
-                                     P(eng.d_class_ids), P(eng.d_src_index), P(eng.d_counts),
-                                     P(eng.d_tiles), st), "gather")
+        N.check(lib.mrx_unmold_prepare(P(d_det), N.MRX_F32, P(d_msk), N.MRX_F32, BATCH, N_INST, 28,
+                                       28, CLASSES, P(eng.d_geom), P(eng.d_boxes),
+                                       P(eng.d_class_ids), P(eng.d_scores), P(eng.d_src_index),
+                                       P(eng.d_box_aux), P(eng.d_counts), P(eng.d_status),
+                                       P(eng.d_tiles), P(eng.d_sched), st), "prepare")
         kev[s][0].record(stream)
-        N.check(lib.mrx_mask_expand(P(eng.d_tiles), P(eng.d_boxes), P(eng.d_box_aux),
+        N.check(lib.mrx_mask_expand(P(eng.d_tiles), P(eng.d_src_index), P(eng.d_boxes),
+                                    P(eng.d_box_aux),
                                     P(eng.d_counts), P(eng.d_geom),
                                     P(eng.d_canvas_off), P(eng.d_canvas), BATCH, N_INST, 28, 28,
                                     eng.chunk_bytes, eng.ctas_per_sm, P(eng.d_sched), st),
@@ -725,10 +723,10 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, **pcie,
                     "path": "engine.StreamingUnmolder: pinned host detections+mrcnn_mask -> H2D "
-                            "(own stream, overlaps the previous batch's D2H) -> 3 kernels -> D2H "
+                            "(own stream, overlaps the previous batch's D2H) -> 2 kernels -> D2H "
                             "of counts, boxes and the [H,W,N] bool canvases; every batch's "
                             "masks are waited for on the host"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "mask_expand_team_kernel",
                          "kernel_ms": k_ms, "kernel_ms_min": float(np.min(expand_ms)),

@@ -8,6 +8,7 @@
  *   mrx_anchors            <- api_utils.get_anchors(image_shape)          serve.py:105
  *   mrx_unmold_prologue    <- api_utils.unmold_detections(...) steps 1-6  serve.py:147-154
  *   mrx_gather_tiles       <- mrcnn_mask[arange(N),:,:,class_ids]         (same call)
+ *   mrx_unmold_prepare     (the two above in one launch)
  *   mrx_mask_expand        <- per-instance unmold_mask + np.stack(axis=-1)(same call)
  *   mrx_mask_expand_values    (parity instrumentation of the kernel above)
  *   mrx_cv2_resize_u8c3[_batch] <- cv2.resize(img, (S, S))                serve.py:88-89
@@ -114,6 +115,17 @@ int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype,
  * it zeroed (no memset between launches).  One scratch per stream of launches. */
 #define MRX_SCHED_WORDS 4
 
+/* mrx_unmold_prologue and mrx_gather_tiles in ONE launch (what the engine uses): the prologue's
+ * outputs as above; the class tiles are stored by ORIGINAL detection row,
+ *   d_tiles[b][t] = float32(mrcnn_mask[b, t, :, :, class_id of row t])      (rows with class 0: untouched)
+ * which needs nothing from the prologue, so both run side by side in the same grid.  The expand
+ * entry points then take d_tile_index = d_src_index (kept instance k -> its row). */
+int mrx_unmold_prepare(const void *d_detections, int det_dtype, const void *d_mrcnn_mask,
+                       int mask_dtype, int B, int R, int mh, int mw, int C,
+                       const int *d_geom, int *d_boxes, int *d_class_ids, void *d_scores,
+                       int *d_src_index, int *d_box_aux, int *d_counts, int *d_status,
+                       float *d_tiles, unsigned int *d_sched, void *stream);
+
 /* The hot kernel.  For every image b writes the bool canvas [H_b, W_b, N_b]
  * (N innermost, 1 byte per element, values 0/1) at d_canvas + d_canvas_off[b]:
  * zero fill, zero-border half-pixel bilinear resize of each tile to its box,
@@ -125,8 +137,12 @@ int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype,
  *   10 rows x N instances; it is raised to the minimum that holds 16 pixels of R
  *   instances per row); multiple of 16, >= 1024; 0 = as large as fits (library default).
  *   ctas_per_sm: used by the generic kernel only (R too large for the tile buffers, or
- *   mask tiles wider than 30 columns); 0 = as many as fit.                           */
-int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
+ *   mask tiles wider than 30 columns); 0 = as many as fit.
+ *   d_tile_index [B,R] int32 or NULL: kept instance k of image b resizes
+ *   d_tiles[b][d_tile_index[b][k]] (NULL: d_tiles[b][k], the layout mrx_gather_tiles writes;
+ *   d_src_index: the layout mrx_unmold_prepare writes).                              */
+int mrx_mask_expand(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
+                    const int *d_box_aux,
                     const int *d_counts, const int *d_geom, const long long *d_canvas_off,
                     unsigned char *d_canvas, int B, int R, int mh, int mw,
                     int chunk_bytes, int ctas_per_sm,
@@ -139,7 +155,8 @@ int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_box_a
  * written.  The canvas is written as usual.  Tests compare these values with the float64
  * oracle (|diff| <= 1e-6).  Shapes the team kernel does not take (R > 200, mask tiles wider
  * than 30 columns) return MRX_E_UNSUPPORTED. */
-int mrx_mask_expand_values(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
+int mrx_mask_expand_values(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
+                           const int *d_box_aux,
                            const int *d_counts, const int *d_geom, const long long *d_canvas_off,
                            unsigned char *d_canvas, float *d_values, int B, int R, int mh, int mw,
                            unsigned int *d_sched, void *stream);
@@ -215,7 +232,8 @@ int mrx_pack_masks(const unsigned char *d_canvas, const long long *d_canvas_off,
  * d_packed may be memory of ANOTHER GPU mapped with mrx_peer_open (fused compute + gather).
  * max_w: widest W_b of the batch.  Mask tiles wider than 30 columns: MRX_E_UNSUPPORTED
  * (use mrx_mask_expand + mrx_pack_masks). */
-int mrx_mask_expand_packed(const float *d_tiles, const int *d_boxes, const int *d_counts,
+int mrx_mask_expand_packed(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
+                           const int *d_counts,
                            const int *d_geom, const long long *d_packed_off,
                            unsigned char *d_packed, int B, int R, int mh, int mw, int max_w,
                            unsigned int *d_sched, void *stream);

@@ -42,7 +42,18 @@ int current_device_info(DevInfo *out) {
 int ensure_dynamic_smem(const void *func, SmemCache *cache, int device, int bytes) {
   std::lock_guard<std::mutex> lock(g_dev_mutex);
   if (cache->set[device] >= bytes) return MRX_OK;
-  MRX_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    cudaFuncAttributes fa;
+    memset(&fa, 0, sizeof(fa));
+    cudaGetLastError();   // do not leave the error pending for the caller's next CUDA call
+    cudaFuncGetAttributes(&fa, func);
+    cudaGetLastError();
+    set_error("cannot opt a kernel into %d B of dynamic shared memory on device %d: %s "
+              "(static %zu B, current max dynamic %d B)",
+              bytes, device, cudaGetErrorString(e), fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
+    return MRX_E_CUDA;
+  }
   cache->set[device] = bytes;
   return MRX_OK;
 }

@@ -18,6 +18,7 @@ struct __align__(16) BoxAux {
 
 struct ExpandParams {
   const float *tiles;           // [B,R,mh,mw]
+  const int *tile_index;        // [B,R] tile of kept instance k = tiles[b][tile_index[b][k]]; NULL: k
   const int4 *boxes;            // [B,R] (y1,x1,y2,x2)
   const BoxAux *aux;            // [B,R]
   const int *counts;            // [B]

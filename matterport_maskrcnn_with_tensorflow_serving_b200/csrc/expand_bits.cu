@@ -12,31 +12,39 @@
 //
 // Work decomposition: a UNIT is `rb` consecutive rows of one instance's plane = rb * WB
 // contiguous bytes (WB = ceil(W/8)).  Warps work alone (no block-level barrier after the
-// prologue): a warp claims a run of consecutive units from a global counter and, per unit,
+// prologue): a warp claims one unit at a time from a global counter and, per unit,
 //   - outside the box rows: one bulk copy (shared -> global, TMA) from the CTA's zero page;
-//   - else: zero its own buffer, then per 32-column block of the box: horizontal source
-//     coordinate of the lane's column once, walk the unit's rows with the vertical source row
-//     advancing by exact integer arithmetic, one FFMA + compare + ballot per row, one 4-byte
-//     (or <= 4 one-byte) shared-memory store of the ballot; lanes are assigned to columns in
-//     packbits order (lane ^ 7) so the ballot IS the output word; then one bulk copy.
+//   - else: zero its own buffer, then per group of four 32-column blocks of the box: horizontal
+//     source coordinate of the lane's column in each block once, then walk the unit's rows --
+//     the vertical source coordinate advances by exact integer arithmetic once per row for the
+//     whole group, each block adds one FFMA + compare + ballot and one 4-byte (or <= 4
+//     one-byte) shared-memory store of the ballot (four independent chains hide each other's
+//     latency); lanes are assigned to columns in packbits order (lane ^ 7) so the ballot IS
+//     the output word; then one bulk copy.
 // Each warp has two buffers so that the store of unit k overlaps the computation of unit k+1.
 // Planes whose row pitch is not a multiple of 16 bytes (W = 1333: WB = 167) keep each unit in
 // shared memory at its global address mod 16; the aligned body goes out as a bulk copy and the
 // <= 15 head / tail bytes as byte stores.  HBM sees every output byte written exactly once.
 //
-// Bound: instruction issue over the in-box samples (~13 warp instructions per row of 32
+// Bound: instruction issue over the in-box samples (~6 warp instructions per row of 32
 // columns) plus 1/8 of the canvas bytes to HBM; see DESIGN.md 3.9 for the measured figures.
+#include <stdlib.h>
+
 #include "expand.cuh"
+
+#ifndef MRX_BITS_WARPS_DEFAULT
+#define MRX_BITS_WARPS_DEFAULT 16
+#endif
 
 namespace mrx {
 
 namespace bits {
 
-constexpr int kWarps = 16;
-constexpr int kRun = 8;   // consecutive units a warp claims per atomic
+constexpr int kGroup = 4;   // column blocks a warp walks side by side (independent chains)
 
 struct BitsParams {
   const float *tiles;            // [B,R,mh,mw]
+  const int *tile_index;         // [B,R] or NULL (see ExpandParams)
   const int4 *boxes;             // [B,R]
   const int *counts;             // [B]
   const int *geom;               // [B,8]
@@ -68,6 +76,7 @@ __device__ __forceinline__ void store_unit(unsigned char *g, const unsigned char
   }
 }
 
+template <int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 mask_expand_bits_kernel(const BitsParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -117,30 +126,33 @@ mask_expand_bits_kernel(const BitsParams p) {
   const int lcol = min(max(lane - 1, 0), mw - 1);
   int cur_b = 0;          // image of the current unit (search cursor, units are claimed in order)
   int cached_b = -1;      // image whose constants are cached below
-  int H = 0, W = 0, N = 0, WB = 0, rb = 1, nbands = 1;
+  int H = 0, W = 0, WB = 0, rb = 1, nbands = 1;
   const float *tiles_b = nullptr;
+  const int *tidx_b = nullptr;
   const int4 *boxes_b = nullptr;
   unsigned char *out_b = nullptr;
   int which = 0;          // buffer the next computed unit uses
 
   while (true) {
+    // one unit per claim: a unit costs anything from one bulk copy (rows outside the box) to
+    // ~50 rows x 16 column blocks of samples, so coarser claims leave a tail of busy warps
     int u0 = 0;
-    if (lane == 0) u0 = static_cast<int>(atomicAdd(p.sched + 2, static_cast<unsigned>(kRun)));
+    if (lane == 0) u0 = static_cast<int>(atomicAdd(p.sched + 2, 1u));
     u0 = __shfl_sync(0xffffffffu, u0, 0);
     if (u0 >= total) break;
-    const int u1 = min(u0 + kRun, total);
-    for (int u = u0; u < u1; ++u) {
+    {
+      const int u = u0;
       while (u >= s_prefix[cur_b + 1]) ++cur_b;
       if (cur_b != cached_b) {
         cached_b = cur_b;
         H = p.geom[cur_b * MRX_GEOM_INTS + 0];
         W = p.geom[cur_b * MRX_GEOM_INTS + 1];
-        N = p.counts[cur_b];
         WB = (W + 7) >> 3;
         rb = unit_rows(WB, ubuf);
         nbands = (H + rb - 1) / rb;
         tiles_b = p.tiles + static_cast<size_t>(cur_b) * p.R * mh * mw;
         boxes_b = p.boxes + static_cast<size_t>(cur_b) * p.R;
+        tidx_b = p.tile_index != nullptr ? p.tile_index + static_cast<size_t>(cur_b) * p.R : nullptr;
         out_b = p.packed + p.packed_off[cur_b];
       }
       const int local = u - s_prefix[cur_b];
@@ -192,7 +204,8 @@ mask_expand_bits_kernel(const BitsParams p) {
       int stepQy = 0;   // source-row advance per canvas row: (2*mh) / Dy and remainder
       if (Dy <= 2 * mh) stepQy = (2 * mh) / Dy;
       const int stepRy = 2 * mh - stepQy * Dy;
-      const float *tp = tiles_b + static_cast<unsigned>(n * mh * mw + lcol);
+      const int tile = tidx_b != nullptr ? __ldg(tidx_b + n) : n;
+      const float *tp = tiles_b + static_cast<unsigned>(tile * mh * mw + lcol);
       auto raw = [&](int j) -> float {   // tile row j in lane-column layout, zero outside the tile
         const float v = __ldg(tp + static_cast<unsigned>(min(max(j, 0), mh - 1) * mw));
         return (lanecol && j >= 0 && j < mh) ? v : 0.f;
@@ -200,13 +213,19 @@ mask_expand_bits_kernel(const BitsParams p) {
       const bool word_ok = ((a | WB) & 3) == 0;   // every ballot word lands 4-byte aligned
       const uint32_t row0_addr = smem_u32(buf) + static_cast<uint32_t>(a + (ya - r0) * WB);
 
-      for (int cb = bx.y >> 5; cb <= (bx.w - 1) >> 5; ++cb) {
-        // lane -> column in packbits order: bit l of the ballot is pixel 8*(l/8) + 7 - l%8
-        const int x = (cb << 5) + (lane ^ 7);
-        const bool colvalid = x >= bx.y && x < bx.w;
-        int idx;
-        float wx;
-        {
+      // kGroup column blocks side by side: the vertical walk (integer coordinate, weight, source
+      // row advance) and the tile row fetches are shared, the per-block chains are independent
+      const int cb_last = (bx.w - 1) >> 5;
+      for (int cb0 = bx.y >> 5; cb0 <= cb_last; cb0 += kGroup) {
+        int idx[kGroup];
+        float wx[kGroup], thr[kGroup], ht[kGroup], hb[kGroup], dh[kGroup];
+        int nbytes[kGroup];
+#pragma unroll
+        for (int c = 0; c < kGroup; ++c) {
+          const int cb = cb0 + c;
+          // lane -> column in packbits order: bit l of the ballot is pixel 8*(l/8) + 7 - l%8
+          const int x = (cb << 5) + (lane ^ 7);
+          const bool colvalid = cb <= cb_last && x >= bx.y && x < bx.w;
           const int A = mw * (2 * (x - bx.y) + 1) - bw;
           int i0 = __float2int_rd(static_cast<float>(A) * invD);
           int rem = A - i0 * D;
@@ -218,40 +237,60 @@ mask_expand_bits_kernel(const BitsParams p) {
             rem -= D;
           }
           // columns outside the box still run the shuffles: keep their lane index in range
-          idx = min(max(i0 + 1, 0), 30);
-          wx = static_cast<float>(rem) * invD;
+          idx[c] = min(max(i0 + 1, 0), 30);
+          wx[c] = static_cast<float>(rem) * invD;
+          thr[c] = colvalid ? 0.5f : __int_as_float(0x7f800000);
+          nbytes[c] = cb <= cb_last ? min(4, WB - (cb << 2)) : 0;   // bytes of the block inside the row
         }
-        auto hrow = [&](float rv) -> float {
-          const float lo = __shfl_sync(0xffffffffu, rv, idx);
-          const float hi = __shfl_sync(0xffffffffu, rv, idx + 1);
-          return fmaf(wx, hi - lo, lo);
+        auto hrow = [&](float rv, int c) -> float {
+          const float lo = __shfl_sync(0xffffffffu, rv, idx[c]);
+          const float hi = __shfl_sync(0xffffffffu, rv, idx[c] + 1);
+          return fmaf(wx[c], hi - lo, lo);
         };
-        const float thr = colvalid ? 0.5f : __int_as_float(0x7f800000);
-        const int nbytes = min(4, WB - (cb << 2));   // bytes of this block inside the row
         int jcur = j_first, j0 = j_first, remy = rem_first;
-        float ht = hrow(raw(jcur)), hb = hrow(raw(jcur + 1));
+        {
+          const float ra = raw(jcur), rbv = raw(jcur + 1);
+#pragma unroll
+          for (int c = 0; c < kGroup; ++c) {
+            ht[c] = hrow(ra, c);
+            hb[c] = hrow(rbv, c);
+            dh[c] = hb[c] - ht[c];
+          }
+        }
         float rawn = raw(jcur + 2);   // fetched one advance ahead
-        float dh = hb - ht;
-        uint32_t addr = row0_addr + static_cast<uint32_t>(cb << 2);
+        uint32_t addr = row0_addr + static_cast<uint32_t>(cb0 << 2);
         for (int r = ya; r < yb; ++r) {
           if (j0 != jcur) {   // warp-uniform
             if (j0 == jcur + 1) {
-              ht = hb;
-              hb = hrow(rawn);
+#pragma unroll
+              for (int c = 0; c < kGroup; ++c) {
+                ht[c] = hb[c];
+                hb[c] = hrow(rawn, c);
+              }
             } else {
-              ht = hrow(raw(j0));
-              hb = hrow(raw(j0 + 1));
+              const float ra = raw(j0), rbv = raw(j0 + 1);
+#pragma unroll
+              for (int c = 0; c < kGroup; ++c) {
+                ht[c] = hrow(ra, c);
+                hb[c] = hrow(rbv, c);
+              }
             }
             jcur = j0;
             rawn = raw(jcur + 2);
-            dh = hb - ht;
+#pragma unroll
+            for (int c = 0; c < kGroup; ++c) dh[c] = hb[c] - ht[c];
           }
-          const float v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
-          const unsigned bal = __ballot_sync(0xffffffffu, v >= thr);
-          if (word_ok) {   // WB % 4 == 0: all four bytes of the block are inside the row
-            if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(bal));
-          } else if (lane < nbytes) {
-            asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + lane), "r"(bal >> (8 * lane)));
+          const float wy = static_cast<float>(remy) * invDy;
+#pragma unroll
+          for (int c = 0; c < kGroup; ++c) {
+            const float v = fmaf(wy, dh[c], ht[c]);
+            const unsigned bal = __ballot_sync(0xffffffffu, v >= thr[c]);
+            const uint32_t ac = addr + 4u * c;
+            if (word_ok) {   // WB % 4 == 0: all four bytes of a block are inside the row
+              if (lane == 0 && nbytes[c] > 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ac), "r"(bal));
+            } else if (lane < nbytes[c]) {
+              asm volatile("st.shared.u8 [%0], %1;" ::"r"(ac + lane), "r"(bal >> (8 * lane)));
+            }
           }
           addr += static_cast<uint32_t>(WB);
           remy += stepRy;
@@ -285,7 +324,28 @@ mask_expand_bits_kernel(const BitsParams p) {
 
 using namespace mrx;
 
-extern "C" int mrx_mask_expand_packed(const float *d_tiles, const int *d_boxes, const int *d_counts,
+template <int kWarps>
+static int launch_bits(mrx::bits::BitsParams prm, const DevInfo &dev, int max_w, cudaStream_t st) {
+  using namespace mrx::bits;
+  const size_t fixed = static_cast<size_t>(prm.B + 1) * sizeof(int) + 1024;   // prefix + static + slack
+  int ubuf = static_cast<int>((static_cast<size_t>(dev.max_smem_optin) - fixed) / (1 + 2 * kWarps)) & ~127;
+  if (ubuf > 8192) ubuf = 8192;
+  const int wb = (max_w + 7) >> 3;
+  MRX_CHECK_SUPPORTED(wb + 16 <= ubuf, "mrx_mask_expand_packed: image %d pixels wide does not fit a "
+                      "unit buffer of %d bytes", max_w, ubuf);
+  prm.ubuf = ubuf;
+  const size_t smem = static_cast<size_t>(ubuf) * (1 + 2 * kWarps) + static_cast<size_t>(prm.B + 1) * sizeof(int);
+  static SmemCache cache;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(mask_expand_bits_kernel<kWarps>), &cache,
+                                   dev.device, static_cast<int>(smem)))
+    return rc;
+  mask_expand_bits_kernel<kWarps><<<dev.sms, kWarps * 32, smem, st>>>(prm);
+  MRX_LAUNCH_CHECK("mask_expand_bits_kernel");
+  return MRX_OK;
+}
+
+extern "C" int mrx_mask_expand_packed(const float *d_tiles, const int *d_tile_index,
+                                      const int *d_boxes, const int *d_counts,
                                       const int *d_geom, const long long *d_packed_off,
                                       unsigned char *d_packed, int B, int R, int mh, int mw,
                                       int max_w, unsigned int *d_sched, void *stream) {
@@ -300,14 +360,9 @@ extern "C" int mrx_mask_expand_packed(const float *d_tiles, const int *d_boxes, 
   if (B == 0) return MRX_OK;
   DevInfo dev;
   if (int rc = current_device_info(&dev)) return rc;
-  const size_t fixed = static_cast<size_t>(B + 1) * sizeof(int) + 64;
-  int ubuf = static_cast<int>((static_cast<size_t>(dev.max_smem_optin) - fixed) / (1 + 2 * kWarps)) & ~127;
-  if (ubuf > 8192) ubuf = 8192;
-  const int wb = (max_w + 7) >> 3;
-  MRX_CHECK_SUPPORTED(wb + 16 <= ubuf, "mrx_mask_expand_packed: image %d pixels wide does not fit a "
-                      "unit buffer of %d bytes", max_w, ubuf);
   BitsParams prm;
   prm.tiles = d_tiles;
+  prm.tile_index = d_tile_index;
   prm.boxes = reinterpret_cast<const int4 *>(d_boxes);
   prm.counts = d_counts;
   prm.geom = d_geom;
@@ -318,13 +373,16 @@ extern "C" int mrx_mask_expand_packed(const float *d_tiles, const int *d_boxes, 
   prm.R = R;
   prm.mh = mh;
   prm.mw = mw;
-  prm.ubuf = ubuf;
-  const size_t smem = static_cast<size_t>(ubuf) * (1 + 2 * kWarps) + static_cast<size_t>(B + 1) * sizeof(int);
-  static SmemCache cache;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(mask_expand_bits_kernel), &cache,
-                                   dev.device, static_cast<int>(smem)))
-    return rc;
-  mask_expand_bits_kernel<<<dev.sms, kWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(prm);
-  MRX_LAUNCH_CHECK("mask_expand_bits_kernel");
-  return MRX_OK;
+  prm.ubuf = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#ifdef MRX_DEV
+  if (const char *e = getenv("MRX_BITS_WARPS")) {
+    const int w = atoi(e);
+    if (w == 8) return launch_bits<8>(prm, dev, max_w, st);
+    if (w == 16) return launch_bits<16>(prm, dev, max_w, st);
+    if (w == 24) return launch_bits<24>(prm, dev, max_w, st);
+    if (w == 32) return launch_bits<32>(prm, dev, max_w, st);
+  }
+#endif
+  return launch_bits<MRX_BITS_WARPS_DEFAULT>(prm, dev, max_w, st);
 }

@@ -64,7 +64,8 @@ constexpr int kCand = 128;   // boxes tested per cull pass == capacity of the en
 // column blocks (written once by the culling lane).
 struct __align__(16) TEntry {
   int x1, x2;    // box columns
-  int npk;       // n | ra << 16 | rb << 22 : instance, first and one-past-last tile row in the box
+  int npk;       // n | tile << 8 | ra << 16 | rb << 22 : instance, its tile's index, first and
+                 // one-past-last tile row in the box
   float invD;    // 1 / (2 * box width)
   int Dy;        // 2 * box height
   float invDy;   // 1 / Dy
@@ -292,7 +293,9 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
       TEntry e;
       e.x1 = bx.y;
       e.x2 = bx.w;
-      e.npk = n | (ra << 16) | (rb << 22);
+      const int tile = p.tile_index != nullptr
+                           ? __ldg(p.tile_index + (jb.boxes_b - p.boxes) + n) : n;
+      e.npk = n | (tile << 8) | (ra << 16) | (rb << 22);
       e.invD = __fdiv_rn(1.0f, static_cast<float>(2 * (bx.w - bx.y)));
       e.Dy = 2 * bh;
       e.invDy = __fdiv_rn(1.0f, static_cast<float>(2 * bh));
@@ -415,7 +418,8 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
         const int4 eb = *(reinterpret_cast<const int4 *>(&s_ent[ei]) + 1);    // Dy, invDy, j0a, remya
         const float invD = __int_as_float(ea.w), invDy = __int_as_float(eb.y);
         const int Dy = eb.x;
-        const int n = ea.z & 0xffff, ra = (ea.z >> 16) & 63, rb = (ea.z >> 22) & 63;
+        const int n = ea.z & 0xff, tile = (ea.z >> 8) & 0xff, ra = (ea.z >> 16) & 63,
+                  rb = (ea.z >> 22) & 63;
         const int x = xc + lane;
         const bool colvalid = x >= xa && x < xb;
         // exact horizontal source coordinate of this lane's column: taps B[idx], B[idx+1] of the
@@ -437,7 +441,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
           idx = i0 + 1;
           wx = static_cast<float>(rem) * invD;
         }
-        const float *tp = tiles_b + static_cast<unsigned>(n * mh * mw + lcol);
+        const float *tp = tiles_b + static_cast<unsigned>(tile * mh * mw + lcol);
         // raw(j): tile row j in lane-column layout (zero outside the tile);
         // hrow(raw): its horizontal interpolation at this lane's canvas column
         auto raw = [&](int j) -> float {
@@ -701,7 +705,8 @@ static int launch_team_cfg(const ExpandParams &prm, const DevInfo &dev, int want
   const int avail = min(static_cast<int>((static_cast<size_t>(max_optin) - fixed) / kTeams), kMaxBuf) & ~127;
   // a tile row must hold 16 pixels of R instances (aligned shapes) / one pixel + alignment shift
   const int need = (max(16 * prm.R, prm.R + 48) * kTileRows + 127) & ~127;
-  if (need > avail) return MRX_E_UNSUPPORTED;   // caller falls back to the generic kernel
+  // (an entry packs the instance and its tile index into 8 bits each)
+  if (need > avail || prm.R > 256) return MRX_E_UNSUPPORTED;   // caller falls back to the generic kernel
   int buf = avail;
   if (want_buf > 0 && want_buf < buf) buf = want_buf & ~127;
   if (buf < need) buf = need;

@@ -7,16 +7,21 @@
 // the reference array exactly.  (mrx_mask_expand_packed, expand_bits.cu, produces the same
 // bytes without ever writing the byte canvas; this kernel serves callers that hold one.)
 //
-// HBM-read bound: N bytes per pixel in, N/8 out.  One CTA = 256 consecutive pixels of one canvas
-// row: their 256*N canvas bytes are contiguous (N innermost) and are staged into shared memory
-// with 16-byte loads, several in flight per thread.  The transpose to bit planes is byte
-// arithmetic, no ballots: a thread takes 8 consecutive pixels x 4 consecutive instances -- eight
-// 32-bit shared-memory words, one per pixel, each holding the 0/1 bytes of the four instances --
-// and folds them with   acc |= (word & 0x01010101) << (7 - k)   into four output bytes, one
-// per instance plane.  Lanes are laid out 4 pixel groups x 8 instance quads so that the eight
-// words of a step fall into 32 different banks (pixel-group stride 8*N bytes = 8 banks at
-// N = 100, instance-quad stride one bank).  Shapes with N % 4 != 0 or rows that are not
-// 4-byte aligned take the same walk one instance (one byte) at a time.
+// HBM-read bound: N bytes per pixel in, N/8 out.  Two kernels, each image goes to one of them:
+//
+// pack_quads_kernel (N % 4 == 0, e.g. the full 100 instances): no shared memory at all.  A thread
+// owns 32 consecutive pixels x 4 consecutive instances: thirty-two independent 4-byte loads
+// (the 0/1 bytes of its four instances at each pixel), folded with
+//     acc[b] |= (word & 0x01010101) << (7 - k)        pixel 8*b + k of the thread's 32
+// into one output byte per (8 pixels, instance), transposed with eight byte permutes into one
+// 32-bit word per instance plane and stored.  Lanes are laid out 4 pixel runs x 8 instance
+// quads, so every load instruction of a warp reads four fully used 32-byte sectors and every
+// store writes 16 contiguous bytes per plane.  (A first version staged 256 pixels in shared
+// memory and re-read them: 2 x 25.6 KB of shared-memory traffic per 25.6 KB of canvas put it at
+// the shared-memory bandwidth, 0.42 of the HBM roofline.)
+//
+// pack_bytes_kernel (any N, any alignment; ragged instance counts): 256 consecutive pixels of a
+// row staged in shared memory at their global address mod 16, then one instance per lane slot.
 #include "common.cuh"
 
 namespace mrx {
@@ -25,7 +30,66 @@ constexpr int kPackThreads = 256;
 constexpr int kPackPixels = 256;
 
 __global__ void __launch_bounds__(kPackThreads)
-pack_masks_kernel(const unsigned char *__restrict__ canvas, const long long *__restrict__ canvas_off,
+pack_quads_kernel(const unsigned char *__restrict__ canvas, const long long *__restrict__ canvas_off,
+                  const int *__restrict__ counts, const int *__restrict__ geom,
+                  unsigned char *__restrict__ packed, const long long *__restrict__ packed_off) {
+  const int b = blockIdx.z;
+  const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
+  const int y = blockIdx.y;
+  const int N = counts[b];
+  if (y >= H || N <= 0 || (N & 3) != 0) return;   // other N: pack_bytes_kernel
+  const int lane = threadIdx.x & 31;
+  const int nquads = N >> 2;
+  const int qblocks = (nquads + 7) >> 3;             // 8 instance quads per warp
+  const int pblocks = (W + 127) >> 7;                // 4 runs of 32 pixels per warp
+  const int wid = blockIdx.x * (kPackThreads / 32) + (threadIdx.x >> 5);
+  if (wid >= pblocks * qblocks) return;
+  const int pb = wid / qblocks, qb = wid - pb * qblocks;
+  const int run = pb * 4 + (lane >> 3);              // which run of 32 pixels of the row
+  const int q = qb * 8 + (lane & 7);
+  const int x0 = run << 5;
+  if (x0 >= W || q >= nquads) return;
+  const int npx = min(32, W - x0);
+  // N % 4 == 0 and 16-byte aligned slots: every (pixel, quad) word is 4-byte aligned
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(
+                            canvas + canvas_off[b] + (static_cast<long long>(y) * W + x0) * N) + q;
+  uint32_t acc[4];
+#pragma unroll
+  for (int bq = 0; bq < 4; ++bq) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int px = 8 * bq + k;
+      w[k] = px < npx ? __ldg(src + static_cast<size_t>(px) * nquads) : 0u;
+    }
+    uint32_t a = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a |= (w[k] & 0x01010101u) << (7 - k);
+    acc[bq] = a;
+  }
+  // acc[bq] byte j = packed byte bq of instance 4q + j  ->  word of instance j = bytes 0..3
+  const uint32_t t0 = __byte_perm(acc[0], acc[1], 0x5140), t1 = __byte_perm(acc[2], acc[3], 0x5140);
+  const uint32_t t2 = __byte_perm(acc[0], acc[1], 0x7362), t3 = __byte_perm(acc[2], acc[3], 0x7362);
+  const uint32_t out[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632),
+                           __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
+  const int wb = (W + 7) >> 3;
+  const long long plane = static_cast<long long>(H) * wb;
+  unsigned char *dst = packed + packed_off[b] + (static_cast<long long>(4 * q) * H + y) * wb + (x0 >> 3);
+  const int nb = min(4, wb - (x0 >> 3));             // bytes of this run inside the packed row
+  const bool word_ok = nb == 4 && ((reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(plane)) & 3u) == 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    unsigned char *o = dst + j * plane;
+    if (word_ok) {
+      *reinterpret_cast<uint32_t *>(o) = out[j];
+    } else {
+      for (int t = 0; t < nb; ++t) o[t] = static_cast<unsigned char>(out[j] >> (8 * t));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPackThreads)
+pack_bytes_kernel(const unsigned char *__restrict__ canvas, const long long *__restrict__ canvas_off,
                   const int *__restrict__ counts, const int *__restrict__ geom,
                   unsigned char *__restrict__ packed, const long long *__restrict__ packed_off) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -34,7 +98,7 @@ pack_masks_kernel(const unsigned char *__restrict__ canvas, const long long *__r
   const int y = blockIdx.y;
   const int x0 = blockIdx.x * kPackPixels;
   const int N = counts[b];
-  if (y >= H || x0 >= W || N <= 0) return;
+  if (y >= H || x0 >= W || N <= 0 || (N & 3) == 0) return;   // N % 4 == 0: pack_quads_kernel
   const int npx = min(kPackPixels, W - x0);
   const int t = threadIdx.x;
 
@@ -67,49 +131,22 @@ pack_masks_kernel(const unsigned char *__restrict__ canvas, const long long *__r
   unsigned char *dst = packed + packed_off[b] + static_cast<long long>(y) * wb + (x0 >> 3);
   const int ngroups = (npx + 7) >> 3;                 // 8-pixel groups = output bytes per plane
   const int lane = t & 31, warp = t >> 5;
-  const int gs = lane >> 3, qs = lane & 7;            // 4 pixel groups x 8 instance slots per warp step
-  if (((N | a) & 3) == 0) {
-    // ---- four instances at a time: 32-bit words
-    const int nquads = N >> 2;
-    const int qblocks = (nquads + 7) >> 3;
-    const int gblocks = (ngroups + 3) >> 2;
-    for (int step = warp; step < gblocks * qblocks; step += kPackThreads / 32) {
-      const int gb = step / qblocks, qb = step - gb * qblocks;
-      const int g = gb * 4 + gs, q = qb * 8 + qs;
-      if (g >= ngroups || q >= nquads) continue;
-      const uint32_t *wp = reinterpret_cast<const uint32_t *>(px0 + static_cast<size_t>(8 * g) * N) + q;
-      const int live = min(8, npx - 8 * g);           // pixels of the group inside the row
-      const int stride = N >> 2;
-      uint32_t acc = 0u;
+  const int gs = lane >> 3, qs = lane & 7;            // 4 pixel groups x 8 instances per warp step
+  const int nblocks = (N + 7) >> 3;
+  const int gblocks = (ngroups + 3) >> 2;
+  for (int step = warp; step < gblocks * nblocks; step += kPackThreads / 32) {
+    const int gb = step / nblocks, nb = step - gb * nblocks;
+    const int g = gb * 4 + gs, n = nb * 8 + qs;
+    if (g >= ngroups || n >= N) continue;
+    const unsigned char *bp = px0 + static_cast<size_t>(8 * g) * N + n;
+    const int live = min(8, npx - 8 * g);
+    unsigned acc = 0u;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t w = (k < live) ? wp[k * stride] : 0u;
-        acc |= (w & 0x01010101u) << (7 - k);
-      }
-      unsigned char *o = dst + g + static_cast<long long>(4 * q) * plane;
-      o[0] = static_cast<unsigned char>(acc);
-      o[plane] = static_cast<unsigned char>(acc >> 8);
-      o[2 * plane] = static_cast<unsigned char>(acc >> 16);
-      o[3 * plane] = static_cast<unsigned char>(acc >> 24);
+    for (int k = 0; k < 8; ++k) {
+      const unsigned v = (k < live) ? bp[k * N] : 0u;
+      acc |= (v & 1u) << (7 - k);
     }
-  } else {
-    // ---- any N, any alignment: one instance per slot
-    const int nblocks = (N + 7) >> 3;
-    const int gblocks = (ngroups + 3) >> 2;
-    for (int step = warp; step < gblocks * nblocks; step += kPackThreads / 32) {
-      const int gb = step / nblocks, nb = step - gb * nblocks;
-      const int g = gb * 4 + gs, n = nb * 8 + qs;
-      if (g >= ngroups || n >= N) continue;
-      const unsigned char *bp = px0 + static_cast<size_t>(8 * g) * N + n;
-      const int live = min(8, npx - 8 * g);
-      unsigned acc = 0u;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const unsigned v = (k < live) ? bp[k * N] : 0u;
-        acc |= (v & 1u) << (7 - k);
-      }
-      dst[g + static_cast<long long>(n) * plane] = static_cast<unsigned char>(acc);
-    }
+    dst[g + static_cast<long long>(n) * plane] = static_cast<unsigned char>(acc);
   }
 }
 
@@ -133,12 +170,23 @@ extern "C" int mrx_pack_masks(const unsigned char *d_canvas, const long long *d_
                       "mrx_pack_masks: R=%d needs %zu B of shared memory (limit %d)", R, smem,
                       dev.max_smem_optin);
   static SmemCache cache;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(pack_masks_kernel), &cache,
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(pack_bytes_kernel), &cache,
                                    dev.device, static_cast<int>(smem)))
     return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // each image is packed by exactly one of the two kernels (N % 4 == 0 or not); the other one's
+  // CTAs for that image return at once
+  {
+    const int max_quads = (R + 3) >> 2;
+    const int warps_per_row = ((max_w + 127) >> 7) * ((max_quads + 7) >> 3);
+    dim3 grid((warps_per_row + kPackThreads / 32 - 1) / (kPackThreads / 32), max_h, B);
+    pack_quads_kernel<<<grid, kPackThreads, 0, st>>>(d_canvas, d_canvas_off, d_counts, d_geom,
+                                                     d_packed, d_packed_off);
+    MRX_LAUNCH_CHECK("pack_quads_kernel");
+  }
   dim3 grid((max_w + kPackPixels - 1) / kPackPixels, max_h, B);
-  pack_masks_kernel<<<grid, kPackThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      d_canvas, d_canvas_off, d_counts, d_geom, d_packed, d_packed_off);
-  MRX_LAUNCH_CHECK("pack_masks_kernel");
+  pack_bytes_kernel<<<grid, kPackThreads, smem, st>>>(d_canvas, d_canvas_off, d_counts, d_geom,
+                                                      d_packed, d_packed_off);
+  MRX_LAUNCH_CHECK("pack_bytes_kernel");
   return MRX_OK;
 }

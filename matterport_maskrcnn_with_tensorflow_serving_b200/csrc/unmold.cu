@@ -56,15 +56,16 @@ __device__ __forceinline__ int denorm_coord(double v, int extent_minus_1, int sh
   return __double2int_rn(t);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kPrologueThreads)
-unmold_prologue_kernel(const T *__restrict__ det, int R, int C,
-                       const int *__restrict__ geom, int *__restrict__ boxes,
-                       int *__restrict__ class_ids, T *__restrict__ scores,
-                       int *__restrict__ src_index, BoxAux *__restrict__ aux, int mw,
-                       int *__restrict__ counts, int *__restrict__ status,
-                       unsigned int *__restrict__ job_counter) {
-  const int b = blockIdx.x;
+// One CTA of kThreads threads does image b (every thread of the CTA must call it).
+template <typename T, int kThreads>
+__device__ __forceinline__ void prologue_body(const int b, const T *__restrict__ det, int R, int C,
+                                              const int *__restrict__ geom, int *__restrict__ boxes,
+                                              int *__restrict__ class_ids, T *__restrict__ scores,
+                                              int *__restrict__ src_index, BoxAux *__restrict__ aux,
+                                              int mw, int *__restrict__ counts,
+                                              int *__restrict__ status,
+                                              unsigned int *__restrict__ job_counter) {
+  constexpr int kPrologueThreads = kThreads;   // (shadows the launch constant inside this body)
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
@@ -161,6 +162,18 @@ unmold_prologue_kernel(const T *__restrict__ det, int R, int C,
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(kPrologueThreads)
+unmold_prologue_kernel(const T *__restrict__ det, int R, int C,
+                       const int *__restrict__ geom, int *__restrict__ boxes,
+                       int *__restrict__ class_ids, T *__restrict__ scores,
+                       int *__restrict__ src_index, BoxAux *__restrict__ aux, int mw,
+                       int *__restrict__ counts, int *__restrict__ status,
+                       unsigned int *__restrict__ job_counter) {
+  prologue_body<T, kPrologueThreads>(blockIdx.x, det, R, C, geom, boxes, class_ids, scores, src_index,
+                                     aux, mw, counts, status, job_counter);
+}
+
 // =====================================================================================
 // class-tile gather: grid (R, B), one CTA per (image, kept instance)
 // =====================================================================================
@@ -180,22 +193,10 @@ __device__ __forceinline__ double ld_strided(const double *p) {
   return v;
 }
 
+// copy the `tile_elems` elements in[0], in[C], in[2C], ... to out[0 .. tile_elems) as float32
 template <typename T>
-__global__ void __launch_bounds__(kGatherThreads)
-gather_tiles_kernel(const T *__restrict__ mask, int R, int tile_elems, int C,
-                    const int *__restrict__ class_ids, const int *__restrict__ src_index,
-                    const int *__restrict__ counts, float *__restrict__ tiles) {
-  const int k = blockIdx.x;
-  const int b = blockIdx.y;
-  if (k >= counts[b]) return;
-  const size_t o = static_cast<size_t>(b) * R + k;
-  int cls = class_ids[o];
-  if (cls < 0) cls += C;               // numpy negative index wrap
-  if (cls < 0 || cls >= C) cls = 0;    // flagged by the prologue; stay in bounds
-  const int src = src_index[o];
-  const T *in = mask + (static_cast<size_t>(b) * R + src) * tile_elems * C + cls;
-  float *out = tiles + o * tile_elems;
-  // every element is its own 32-byte sector (stride C): keep four loads in flight per thread
+__device__ __forceinline__ void gather_strided(const T *__restrict__ in, int tile_elems, int C,
+                                               float *__restrict__ out) {  // every element is its own 32-byte sector (stride C): keep four loads in flight per thread
   for (int p0 = threadIdx.x; p0 < tile_elems; p0 += 4 * kGatherThreads) {
     T v[4];
 #pragma unroll
@@ -209,6 +210,51 @@ gather_tiles_kernel(const T *__restrict__ mask, int R, int tile_elems, int C,
       if (p < tile_elems) out[p] = static_cast<float>(v[k]);
     }
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_tiles_kernel(const T *__restrict__ mask, int R, int tile_elems, int C,
+                    const int *__restrict__ class_ids, const int *__restrict__ src_index,
+                    const int *__restrict__ counts, float *__restrict__ tiles) {
+  const int k = blockIdx.x;
+  const int b = blockIdx.y;
+  if (k >= counts[b]) return;
+  const size_t o = static_cast<size_t>(b) * R + k;
+  int cls = class_ids[o];
+  if (cls < 0) cls += C;               // numpy negative index wrap
+  if (cls < 0 || cls >= C) cls = 0;    // flagged by the prologue; stay in bounds
+  const int src = src_index[o];
+  gather_strided(mask + (static_cast<size_t>(b) * R + src) * tile_elems * C + cls, tile_elems, C,
+                 tiles + o * tile_elems);
+}
+
+// One launch for steps 1-6 AND the class-tile gather (the two do not depend on each other when
+// the tiles are stored by ORIGINAL detection row): grid (R + 1, B); CTA (t < R, b) copies the
+// tile of row t's own class -- rows with class_id == 0 can never be kept (the first of them ends
+// the list) and are skipped -- and CTA (R, b) runs the prologue of image b.  The expand kernels
+// then find instance k's tile through src_index[b][k].
+template <typename TD, typename TM>
+__global__ void __launch_bounds__(kGatherThreads)
+unmold_prepare_kernel(const TD *__restrict__ det, const TM *__restrict__ mask, int R, int C,
+                      int tile_elems, const int *__restrict__ geom, int *__restrict__ boxes,
+                      int *__restrict__ class_ids, TD *__restrict__ scores,
+                      int *__restrict__ src_index, BoxAux *__restrict__ aux, int mw,
+                      int *__restrict__ counts, int *__restrict__ status,
+                      unsigned int *__restrict__ job_counter, float *__restrict__ tiles) {
+  const int b = blockIdx.y;
+  if (static_cast<int>(blockIdx.x) == R) {
+    prologue_body<TD, kGatherThreads>(b, det, R, C, geom, boxes, class_ids, scores, src_index, aux, mw,
+                                      counts, status, job_counter);
+    return;
+  }
+  const int t = blockIdx.x;
+  int cls = static_cast<int>(det[(static_cast<size_t>(b) * R + t) * 6 + 4]);   // astype(int32)
+  if (cls == 0) return;
+  if (cls < 0) cls += C;
+  if (cls < 0 || cls >= C) cls = 0;    // flagged by the prologue; stay in bounds
+  gather_strided(mask + (static_cast<size_t>(b) * R + t) * tile_elems * C + cls, tile_elems, C,
+                 tiles + (static_cast<size_t>(b) * R + t) * tile_elems);
 }
 
 // =====================================================================================
@@ -384,12 +430,13 @@ mask_expand_kernel(const ExpandParams p) {
         const int pr = p0 + tid;
         bool valid = false;
         Entry e;
-        int jc = 0, n = 0;
+        int jc = 0, n = 0, tile = 0;
         if (pr < J.n_pairs) {
           const int dr = pr / J.N;
           n = pr - dr * J.N;
           const int row = J.r0 + dr;
           const int4 bx = __ldg(J.boxes_b + n);   // (y1, x1, y2, x2)
+          tile = p.tile_index != nullptr ? __ldg(p.tile_index + (J.boxes_b - p.boxes) + n) : n;
           const int xlo = max(0, J.g0 - row * J.W);
           const int xhi = min(J.W, J.g1 + 1 - row * J.W);
           const int xa = max(xlo, bx.y);
@@ -413,7 +460,7 @@ mask_expand_kernel(const ExpandParams p) {
             e.wy = __fdiv_rn(static_cast<float>(Ay - j0 * Dy), static_cast<float>(Dy));
             e.otop = (j0 < 0) ? -1 : (j0 - jc) * mw;
             e.obot = (j0 + 1 > mh - 1) ? -1 : (j0 + 1 - jc) * mw;
-            e.src_off = (n * mh + jc) * mw;
+            e.src_off = (tile * mh + jc) * mw;
           }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -426,7 +473,7 @@ mask_expand_kernel(const ExpandParams p) {
           // ---- 2a. stage tile rows jc, jc+1
           if (!(p.flags & 1))
             bulk_g2s(s_stage + slot * slot_floats,
-                     J.tiles_b + (static_cast<size_t>(n) * mh + jc) * mw, slot_bytes, &s_bar);
+                     J.tiles_b + (static_cast<size_t>(tile) * mh + jc) * mw, slot_bytes, &s_bar);
         }
       }
       if (tid == 0) s_next = 0;
@@ -599,6 +646,38 @@ extern "C" int mrx_unmold_prologue(const void *d_detections, int det_dtype, int 
   return MRX_OK;
 }
 
+extern "C" int mrx_unmold_prepare(const void *d_detections, int det_dtype, const void *d_mrcnn_mask,
+                                  int mask_dtype, int B, int R, int mh, int mw, int C,
+                                  const int *d_geom, int *d_boxes, int *d_class_ids, void *d_scores,
+                                  int *d_src_index, int *d_box_aux, int *d_counts, int *d_status,
+                                  float *d_tiles, unsigned int *d_sched, void *stream) {
+  MRX_CHECK_ARG(d_detections && d_mrcnn_mask && d_geom && d_boxes && d_class_ids && d_scores &&
+                    d_src_index && d_box_aux && d_counts && d_status && d_tiles,
+                "mrx_unmold_prepare: null pointer");
+  MRX_CHECK_ARG(B >= 0 && B <= 65535 && R >= 1 && R <= 65534 && C >= 1 && mh >= 1 && mw >= 1 &&
+                    mw <= MRX_MAX_MASK_DIM,
+                "mrx_unmold_prepare: bad sizes B=%d R=%d C=%d tile %dx%d", B, R, C, mh, mw);
+  MRX_CHECK_ARG((det_dtype == MRX_F32 || det_dtype == MRX_F64) &&
+                    (mask_dtype == MRX_F32 || mask_dtype == MRX_F64),
+                "mrx_unmold_prepare: dtypes %d / %d", det_dtype, mask_dtype);
+  if (B == 0) return MRX_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(R + 1, B);
+  BoxAux *aux = reinterpret_cast<BoxAux *>(d_box_aux);
+#define MRX_PREPARE(TD, TM)                                                                      \
+  unmold_prepare_kernel<TD, TM><<<grid, kGatherThreads, 0, st>>>(                                \
+      static_cast<const TD *>(d_detections), static_cast<const TM *>(d_mrcnn_mask), R, C, mh * mw, \
+      d_geom, d_boxes, d_class_ids, static_cast<TD *>(d_scores), d_src_index, aux, mw, d_counts,  \
+      d_status, d_sched, d_tiles)
+  if (det_dtype == MRX_F64 && mask_dtype == MRX_F64) MRX_PREPARE(double, double);
+  else if (det_dtype == MRX_F64) MRX_PREPARE(double, float);
+  else if (mask_dtype == MRX_F64) MRX_PREPARE(float, double);
+  else MRX_PREPARE(float, float);
+#undef MRX_PREPARE
+  MRX_LAUNCH_CHECK("unmold_prepare_kernel");
+  return MRX_OK;
+}
+
 extern "C" int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype, int B, int R, int mh,
                                 int mw, int C, const int *d_class_ids, const int *d_src_index,
                                 const int *d_counts, float *d_tiles, void *stream) {
@@ -625,7 +704,8 @@ extern "C" int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype, int B,
   return MRX_OK;
 }
 
-static int mask_expand_impl(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
+static int mask_expand_impl(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
+                            const int *d_box_aux,
                             const int *d_counts, const int *d_geom, const long long *d_canvas_off,
                             unsigned char *d_canvas, float *d_values, int B, int R, int mh, int mw,
                             int chunk_bytes, int ctas_per_sm, unsigned int *d_sched,
@@ -647,6 +727,7 @@ static int mask_expand_impl(const float *d_tiles, const int *d_boxes, const int 
 
   ExpandParams prm;
   prm.tiles = d_tiles;
+  prm.tile_index = d_tile_index;
   prm.boxes = reinterpret_cast<const int4 *>(d_boxes);
   prm.aux = reinterpret_cast<const BoxAux *>(d_box_aux);
   prm.counts = d_counts;
@@ -701,21 +782,21 @@ static int mask_expand_impl(const float *d_tiles, const int *d_boxes, const int 
   return MRX_OK;
 }
 
-extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_boxes, const int *d_box_aux,
-                               const int *d_counts, const int *d_geom,
+extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
+                               const int *d_box_aux, const int *d_counts, const int *d_geom,
                                const long long *d_canvas_off, unsigned char *d_canvas, int B,
                                int R, int mh, int mw, int chunk_bytes, int ctas_per_sm,
                                unsigned int *d_sched, void *stream) {
-  return mask_expand_impl(d_tiles, d_boxes, d_box_aux, d_counts, d_geom, d_canvas_off, d_canvas,
-                          nullptr, B, R, mh, mw, chunk_bytes, ctas_per_sm, d_sched, stream);
+  return mask_expand_impl(d_tiles, d_tile_index, d_boxes, d_box_aux, d_counts, d_geom, d_canvas_off,
+                          d_canvas, nullptr, B, R, mh, mw, chunk_bytes, ctas_per_sm, d_sched, stream);
 }
 
-extern "C" int mrx_mask_expand_values(const float *d_tiles, const int *d_boxes,
-                                      const int *d_box_aux, const int *d_counts,
+extern "C" int mrx_mask_expand_values(const float *d_tiles, const int *d_tile_index,
+                                      const int *d_boxes, const int *d_box_aux, const int *d_counts,
                                       const int *d_geom, const long long *d_canvas_off,
                                       unsigned char *d_canvas, float *d_values, int B, int R,
                                       int mh, int mw, unsigned int *d_sched, void *stream) {
   MRX_CHECK_ARG(d_values != nullptr, "mrx_mask_expand_values: null pointer");
-  return mask_expand_impl(d_tiles, d_boxes, d_box_aux, d_counts, d_geom, d_canvas_off, d_canvas,
-                          d_values, B, R, mh, mw, 0, 0, d_sched, stream);
+  return mask_expand_impl(d_tiles, d_tile_index, d_boxes, d_box_aux, d_counts, d_geom, d_canvas_off,
+                          d_canvas, d_values, B, R, mh, mw, 0, 0, d_sched, stream);
 }

@@ -175,17 +175,15 @@ class UnmoldEngine:
         if not (d_detections.is_contiguous() and d_mrcnn_mask.is_contiguous()):
             raise ValueError("inputs must be contiguous")
         st = N.stream_ptr(stream)
-        lib = self.lib
-        N.check(lib.mrx_unmold_prologue(
-            _ptr(d_detections), _dtype_code(self.det_dtype), n, self.R, self.C, self.mw,
-            _ptr(self.d_geom), _ptr(self.d_boxes), _ptr(self.d_class_ids),
-            _ptr(self.d_scores), _ptr(self.d_src_index), _ptr(self.d_box_aux),
-            _ptr(self.d_counts), _ptr(self.d_status), _ptr(self.d_sched), st),
-            "mrx_unmold_prologue")
-        N.check(lib.mrx_gather_tiles(
-            _ptr(d_mrcnn_mask), _dtype_code(self.mask_dtype), n, self.R, self.mh, self.mw,
-            self.C, _ptr(self.d_class_ids), _ptr(self.d_src_index), _ptr(self.d_counts),
-            _ptr(self.d_tiles), st), "mrx_gather_tiles")
+        # steps 1-6 and the class-tile gather in one launch; tiles are stored by detection row
+        # and found through d_src_index by the expand kernels
+        N.check(self.lib.mrx_unmold_prepare(
+            _ptr(d_detections), _dtype_code(self.det_dtype), _ptr(d_mrcnn_mask),
+            _dtype_code(self.mask_dtype), n, self.R, self.mh, self.mw, self.C,
+            _ptr(self.d_geom), _ptr(self.d_boxes), _ptr(self.d_class_ids), _ptr(self.d_scores),
+            _ptr(self.d_src_index), _ptr(self.d_box_aux), _ptr(self.d_counts),
+            _ptr(self.d_status), _ptr(self.d_tiles), _ptr(self.d_sched), st),
+            "mrx_unmold_prepare")
         if expand:
             self.enqueue_expand(stream)
 
@@ -200,7 +198,8 @@ class UnmoldEngine:
             return
         base = _ptr(self.d_canvas) if canvas_ptr is None else C.c_void_p(int(canvas_ptr))
         N.check(self.lib.mrx_mask_expand(
-            _ptr(self.d_tiles[b0:]), _ptr(self.d_boxes[b0:]), _ptr(self.d_box_aux[b0:]),
+            _ptr(self.d_tiles[b0:]), _ptr(self.d_src_index[b0:]), _ptr(self.d_boxes[b0:]),
+            _ptr(self.d_box_aux[b0:]),
             _ptr(self.d_counts[b0:]), _ptr(self.d_geom[b0:]),
             _ptr(self.d_canvas_off[b0:]), base, b1 - b0, self.R, self.mh, self.mw,
             self.chunk_bytes, self.ctas_per_sm, _ptr(self.d_sched),
@@ -213,7 +212,8 @@ class UnmoldEngine:
         if d_values.dtype != _torch().float32 or d_values.numel() < int(self._offsets[n]):
             raise ValueError("d_values must be float32 with one element per canvas byte")
         N.check(self.lib.mrx_mask_expand_values(
-            _ptr(self.d_tiles), _ptr(self.d_boxes), _ptr(self.d_box_aux), _ptr(self.d_counts),
+            _ptr(self.d_tiles), _ptr(self.d_src_index), _ptr(self.d_boxes), _ptr(self.d_box_aux),
+            _ptr(self.d_counts),
             _ptr(self.d_geom), _ptr(self.d_canvas_off), _ptr(self.d_canvas), _ptr(d_values),
             n, self.R, self.mh, self.mw, _ptr(self.d_sched), N.stream_ptr(stream)),
             "mrx_mask_expand_values")
@@ -258,7 +258,8 @@ class UnmoldEngine:
         g = self._geom_host
         if b1 > b0:
             N.check(self.lib.mrx_mask_expand_packed(
-                _ptr(self.d_tiles[b0:]), _ptr(self.d_boxes[b0:]), _ptr(self.d_counts[b0:]),
+                _ptr(self.d_tiles[b0:]), _ptr(self.d_src_index[b0:]), _ptr(self.d_boxes[b0:]),
+                _ptr(self.d_counts[b0:]),
                 _ptr(self.d_geom[b0:]), _ptr(self.d_packed_off[b0:]), base, b1 - b0, self.R,
                 self.mh, self.mw, int(g[:, 1].max()), _ptr(self.d_sched), N.stream_ptr(stream)),
                 "mrx_mask_expand_packed")
@@ -532,7 +533,7 @@ class StreamingUnmolder:
         self.eng = engine
         self.packed = bool(packed)
         self.zero_copy = mask_upload == "zero_copy"
-        engine.plan(geoms, canvas=not self.packed)
+        engine.plan(geoms, canvas=False)       # the outputs live here, double-buffered
         n = engine._n_images
         self.n = n
         dev = engine.device
@@ -541,19 +542,21 @@ class StreamingUnmolder:
         self.d_msk = None if self.zero_copy else [
             torch.empty((n, engine.R, engine.mh, engine.mw, engine.C), dtype=msk_t, device=dev)
             for _ in range(2)]
-        if self.packed:
-            self.total = engine.packed_layout()[1]
-            engine._packed_buffer()
-        else:
-            self.total = int(engine._offsets[n])
+        self.total = engine.packed_layout()[1] if self.packed else int(engine._offsets[n])
+        self.d_out = [torch.empty((self.total,), dtype=torch.uint8, device=dev) for _ in range(2)]
         self.h_out = [torch.empty((self.total,), dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.h_counts = [torch.empty((n,), dtype=torch.int32).pin_memory() for _ in range(2)]
         self.h_boxes = [torch.empty((n, engine.R, 4), dtype=torch.int32).pin_memory()
                         for _ in range(2)]
-        self.copy_stream = torch.cuda.Stream(device=dev)
+        # three streams: inputs up, kernels, results down -- batch k's download overlaps batch
+        # k+1's kernels and batch k+2's upload (PCIe is full duplex)
+        self.in_stream = torch.cuda.Stream(device=dev)
+        self.out_stream = torch.cuda.Stream(device=dev)
         self.main_stream = torch.cuda.current_stream(dev)
         self.h2d_done = [torch.cuda.Event() for _ in range(2)]
         self.in_free = [torch.cuda.Event() for _ in range(2)]
+        self.out_ready = [torch.cuda.Event() for _ in range(2)]
+        self.out_free = [torch.cuda.Event() for _ in range(2)]
         self.out_done = {}
         self.k = 0
         msk_bytes = n * engine.R * engine.mh * engine.mw * engine.C * engine.mask_dtype.itemsize
@@ -564,33 +567,43 @@ class StreamingUnmolder:
         self.d2h_bytes = self.total + 4 * (n + 4 * n * engine.R)
 
     def submit(self, h_det, h_msk):
+        """Queue one batch (pinned host tensors).  The host buffers of batch k are reused by
+        batch k+2: consume `wait(k)`'s result before submitting batch k+2."""
         torch = _torch()
         k, i = self.k, self.k % 2
-        with torch.cuda.stream(self.copy_stream):
+        eng = self.eng
+        if self.zero_copy and not h_msk.is_pinned():
+            raise ValueError("zero_copy needs the mask tensor in pinned host memory")
+        with torch.cuda.stream(self.in_stream):
             if k >= 2:
-                self.copy_stream.wait_event(self.in_free[i])     # kernels of batch k-2 read d_*[i]
+                self.in_stream.wait_event(self.in_free[i])     # kernels of batch k-2 read d_*[i]
             self.d_det[i].copy_(h_det, non_blocking=True)
             if not self.zero_copy:
                 self.d_msk[i].copy_(h_msk, non_blocking=True)
-            self.h2d_done[i].record(self.copy_stream)
+            self.h2d_done[i].record(self.in_stream)
         ms = self.main_stream
         ms.wait_event(self.h2d_done[i])
+        if k >= 2:
+            ms.wait_event(self.out_free[i])                    # download of batch k-2 read d_out[i]
         msk = h_msk if self.zero_copy else self.d_msk[i]
-        if self.zero_copy and not h_msk.is_pinned():
-            raise ValueError("zero_copy needs the mask tensor in pinned host memory")
-        # (also orders after batch k-1's D2H, which reads the output buffer this batch rewrites)
+        eng.enqueue(self.d_det[i], msk, ms, expand=False)
         if self.packed:
-            self.eng.enqueue_packed(self.d_det[i], msk, ms)
-            d_out = self.eng.d_packed
+            eng.enqueue_expand_packed(ms, packed_ptr=self.d_out[i].data_ptr())
         else:
-            self.eng.enqueue(self.d_det[i], msk, ms)
-            d_out = self.eng.d_canvas
+            eng.enqueue_expand(ms, canvas_ptr=self.d_out[i].data_ptr())
         self.in_free[i].record(ms)
-        self.h_counts[i].copy_(self.eng.d_counts[:self.n], non_blocking=True)
-        self.h_boxes[i].copy_(self.eng.d_boxes[:self.n], non_blocking=True)
-        self.h_out[i].copy_(d_out[:self.total], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(ms)
+        # counts / boxes are single-buffered in the engine: copy them (50 KB) before the next
+        # batch's prologue overwrites them, on the kernel stream
+        with torch.cuda.stream(ms):
+            self.h_counts[i].copy_(eng.d_counts[:self.n], non_blocking=True)
+            self.h_boxes[i].copy_(eng.d_boxes[:self.n], non_blocking=True)
+        self.out_ready[i].record(ms)
+        with torch.cuda.stream(self.out_stream):
+            self.out_stream.wait_event(self.out_ready[i])
+            self.h_out[i].copy_(self.d_out[i], non_blocking=True)
+            self.out_free[i].record(self.out_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.out_stream)
         self.out_done[k] = ev
         self.k += 1
         return k

@@ -179,7 +179,7 @@ def test_chunk_size_independent(cuda_device, chunk):
         assert compare_masks(m, rm, rz, rb)[0] == 0
 
 
-def _run_with_values(ims, R, classes, dtype=np.float32):
+def _run_with_values(ims, R, classes, dtype=np.float64):
     """Batch through the PRODUCTION expand kernel's instrumented instantiation
     (mrx_mask_expand_values: same template, same cull / hrow / walk code).  Returns per image
     (boxes, class_ids, masks bool [H,W,N], values float32 [H,W,N])."""
@@ -210,7 +210,7 @@ def _run_with_values(ims, R, classes, dtype=np.float32):
     return out
 
 
-def _check_values(name, ims, R, classes, dtype=np.float32):
+def _check_values(name, ims, R, classes, dtype=np.float64):
     """Pre-threshold samples of the production kernel vs the float64 oracle, every instance of
     every image: |gpu - oracle| <= 1e-6; masks equal outside the band; stats recorded."""
     got = _run_with_values(ims, R, classes, dtype)

@@ -25,6 +25,15 @@ def child(args):
     from matterport_maskrcnn_with_tensorflow_serving_b200.engine import UnmoldEngine, make_geom
 
     torch.cuda.set_device(0)
+    gran = os.environ.get("MRX_L2_GRAN")
+    if gran:      # experiment: cudaLimitMaxL2FetchGranularity (0x05), a hint in bytes
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        torch.zeros(1, device="cuda")
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(gran)))
+        val = ctypes.c_size_t(0)
+        rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+        print(json.dumps({"l2_fetch_granularity_set": int(gran), "rc": rc, "now": val.value}), flush=True)
     ims = bench.make_bench_images(0, args.batch)
     d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
     d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
@@ -57,6 +66,8 @@ def child(args):
     pack_med, _ = timeit(lambda: eng.pack_masks())
     print(json.dumps({"variant": os.environ.get("MRX_EXPAND_TEAMS", "default"),
                       "flags": os.environ.get("MRX_EXPAND_FLAGS", ""),
+                      "bits_warps": os.environ.get("MRX_BITS_WARPS", "default"),
+                      "l2_gran": os.environ.get("MRX_L2_GRAN", ""),
                       "expand_ms": round(exp_med, 4), "expand_ms_min": round(exp_min, 4),
                       "expand_GBps": round(nbytes / exp_med / 1e6, 1), "step_ms": round(step_med, 4),
                       "prologue_gather_ms": round(pre_med, 4),
@@ -70,17 +81,25 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--variants", nargs="*", default=["6x5x10w0", "6x5x10w1"])
     ap.add_argument("--flags", nargs="*", default=[""])
+    ap.add_argument("--bits-warps", nargs="*", default=[""])
+    ap.add_argument("--l2-gran", nargs="*", default=[""])
     ap.add_argument("--child", action="store_true")
     args = ap.parse_args()
     if args.child:
         return child(args)
     for v in args.variants:
         for f in args.flags:
-            env = dict(os.environ, MRX_EXPAND_TEAMS=v)
-            if f:
-                env["MRX_EXPAND_FLAGS"] = f
-            subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--batch",
-                            str(args.batch), "--iters", str(args.iters)], env=env, check=False)
+            for bw in args.bits_warps:
+                for g in args.l2_gran:
+                    env = dict(os.environ, MRX_EXPAND_TEAMS=v)
+                    if f:
+                        env["MRX_EXPAND_FLAGS"] = f
+                    if bw:
+                        env["MRX_BITS_WARPS"] = bw
+                    if g:
+                        env["MRX_L2_GRAN"] = g
+                    subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--batch",
+                                    str(args.batch), "--iters", str(args.iters)], env=env, check=False)
 
 
 if __name__ == "__main__":
