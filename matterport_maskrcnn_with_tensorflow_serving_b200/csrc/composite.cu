@@ -14,19 +14,47 @@
 // pixel t's N bytes (4 at a time when N % 4 == 0: most words are zero) and applies the
 // blends of the set instances in instance order -- fp64 with explicit _rn intrinsics in
 // NumPy's operation order, truncation to uint32 after every instance: bit-exact.
+//
+// Two forms of the blend, same result:
+//   exact   v = uint32(float64(v) * (1 - alpha) + blend[i][c]) evaluated per set (pixel, instance):
+//           twelve fp64-pipe instructions per blend, any alpha / colours (values may leave 0..255);
+//   table   when every blend keeps values inside 0..255 (alpha and colours in [0, 1]: what
+//           display_instances passes) the step is a function of (instance, channel, v) only:
+//           composite_lut_kernel evaluates the SAME fp64 expression once per (b, i, c, v) --
+//           768 bytes per instance, identity rows for skipped instances -- and the pixel walk
+//           does three byte loads per blend from that table (L1-resident) instead.
 #include "common.cuh"
 
 namespace mrx {
 
 constexpr int kCompThreads = 256;
 
+// lut[b][i][c][v] = uint8 of the blend of instance i, channel c, applied to value v
+__global__ void __launch_bounds__(256)
+composite_lut_kernel(const int *__restrict__ counts, const int4 *__restrict__ boxes,
+                     const double *__restrict__ blend, double one_minus_alpha,
+                     unsigned char *__restrict__ lut, int R) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  if (i >= counts[b]) return;
+  const int4 bx = boxes[static_cast<size_t>(b) * R + i];
+  const bool skip = (bx.x | bx.y | bx.z | bx.w) == 0;   // upstream: `if not np.any(boxes[i]): continue`
+  const unsigned v = threadIdx.x;
+  for (int c = 0; c < 3; ++c) {
+    const double bl = blend[(static_cast<size_t>(b) * R + i) * 3 + c];
+    const unsigned r = __double2uint_rz(__dadd_rn(__dmul_rn(static_cast<double>(v), one_minus_alpha), bl));
+    lut[((static_cast<size_t>(b) * R + i) * 3 + c) * 256 + v] = static_cast<unsigned char>(skip ? v : r);
+  }
+}
+
+template <bool kLut>
 __global__ void __launch_bounds__(kCompThreads)
 composite_masks_kernel(const unsigned char *__restrict__ canvas,
                        const long long *__restrict__ canvas_off,
                        const int *__restrict__ counts, const int *__restrict__ geom,
                        const int4 *__restrict__ boxes, const unsigned char *__restrict__ images,
                        const long long *__restrict__ image_off, const double *__restrict__ blend,
-                       double one_minus_alpha, unsigned char *__restrict__ out, int R) {
+                       double one_minus_alpha, const unsigned char *__restrict__ lut,
+                       unsigned char *__restrict__ out, int R) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.y;
   const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
@@ -42,11 +70,13 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   unsigned char *s_skip = smem + ((static_cast<size_t>(R) * 3 * sizeof(double) + 15) & ~static_cast<size_t>(15));
   unsigned char *s_can = s_skip + ((R + 15) & ~15);
 
-  for (int i = t; i < N * 3; i += kCompThreads)
-    s_blend[i] = blend[static_cast<size_t>(b) * R * 3 + i];
-  for (int i = t; i < N; i += kCompThreads) {
-    const int4 bx = boxes[static_cast<size_t>(b) * R + i];
-    s_skip[i] = (bx.x | bx.y | bx.z | bx.w) == 0;   // upstream: `if not np.any(boxes[i]): continue`
+  if (!kLut) {
+    for (int i = t; i < N * 3; i += kCompThreads)
+      s_blend[i] = blend[static_cast<size_t>(b) * R * 3 + i];
+    for (int i = t; i < N; i += kCompThreads) {
+      const int4 bx = boxes[static_cast<size_t>(b) * R + i];
+      s_skip[i] = (bx.x | bx.y | bx.z | bx.w) == 0;   // upstream: `if not np.any(boxes[i]): continue`
+    }
   }
   if (N > 0) {
     // 256*N is a multiple of 16 and so is every canvas slot offset: whole uint4 loads; the
@@ -72,7 +102,15 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
 
   const unsigned char *ip = images + image_off[b] + (p0 + t) * 3;
   unsigned v0 = ip[0], v1 = ip[1], v2 = ip[2];
+  const unsigned char *lut_b = kLut ? lut + static_cast<size_t>(b) * R * 768 : nullptr;
   auto apply = [&](int i) {
+    if (kLut) {   // same fp64 expression, evaluated once per (instance, channel, value)
+      const unsigned char *l = lut_b + i * 768;
+      v0 = __ldg(l + v0);
+      v1 = __ldg(l + 256 + v1);
+      v2 = __ldg(l + 512 + v2);
+      return;
+    }
     if (s_skip[i]) return;
     const double *bl = s_blend + i * 3;
     v0 = __double2uint_rz(__dadd_rn(__dmul_rn(static_cast<double>(v0), one_minus_alpha), bl[0]));
@@ -119,8 +157,8 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
                                    const int *d_counts, const int *d_geom, const int *d_boxes,
                                    const unsigned char *d_images, const long long *d_image_off,
                                    const double *d_blend, double one_minus_alpha,
-                                   unsigned char *d_out, int B, int R, long long max_pixels,
-                                   void *stream) {
+                                   unsigned char *d_lut, unsigned char *d_out, int B, int R,
+                                   long long max_pixels, void *stream) {
   using namespace mrx;
   MRX_CHECK_ARG(d_canvas && d_canvas_off && d_counts && d_geom && d_boxes && d_images &&
                     d_image_off && d_blend && d_out,
@@ -128,9 +166,9 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
   MRX_CHECK_ARG(B >= 0 && B <= MRX_MAX_BATCH && R >= 1 && max_pixels >= 0,
                 "mrx_composite_masks: bad sizes B=%d R=%d", B, R);
   if (B == 0 || max_pixels == 0) return MRX_OK;
-  int dev = 0, max_optin = 0;
-  MRX_CUDA(cudaGetDevice(&dev));
-  MRX_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  DevInfo dev;
+  if (int rc = current_device_info(&dev)) return rc;
+  const int max_optin = dev.max_smem_optin;
   const size_t smem = ((static_cast<size_t>(R) * 3 * sizeof(double) + 15) & ~static_cast<size_t>(15)) +
                       ((R + 15) & ~15) + static_cast<size_t>(kCompThreads) * R + 16;
   MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(max_optin),
@@ -138,12 +176,28 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
                       max_optin);
   const long long blocks = (max_pixels + kCompThreads - 1) / kCompThreads;
   MRX_CHECK_SUPPORTED(blocks <= 0x7fffffffLL, "mrx_composite_masks: image too large");
-  MRX_CUDA(cudaFuncSetAttribute(composite_masks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(B));
-  composite_masks_kernel<<<grid, kCompThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      d_canvas, d_canvas_off, d_counts, d_geom, reinterpret_cast<const int4 *>(d_boxes), d_images,
-      d_image_off, d_blend, one_minus_alpha, d_out, R);
+  const int4 *boxes4 = reinterpret_cast<const int4 *>(d_boxes);
+  if (d_lut != nullptr) {
+    composite_lut_kernel<<<dim3(R, B), 256, 0, st>>>(d_counts, boxes4, d_blend, one_minus_alpha, d_lut, R);
+    MRX_LAUNCH_CHECK("composite_lut_kernel");
+    static SmemCache cache;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(composite_masks_kernel<true>), &cache,
+                                     dev.device, static_cast<int>(smem)))
+      return rc;
+    composite_masks_kernel<true><<<grid, kCompThreads, smem, st>>>(
+        d_canvas, d_canvas_off, d_counts, d_geom, boxes4, d_images, d_image_off, d_blend,
+        one_minus_alpha, d_lut, d_out, R);
+  } else {
+    static SmemCache cache;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(composite_masks_kernel<false>), &cache,
+                                     dev.device, static_cast<int>(smem)))
+      return rc;
+    composite_masks_kernel<false><<<grid, kCompThreads, smem, st>>>(
+        d_canvas, d_canvas_off, d_counts, d_geom, boxes4, d_images, d_image_off, d_blend,
+        one_minus_alpha, nullptr, d_out, R);
+  }
   MRX_LAUNCH_CHECK("composite_masks_kernel");
   return MRX_OK;
 }

@@ -45,16 +45,27 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def _table_is_valid(tab, alpha):
+    """The tabulated form of the blend (mrx_composite_masks with d_lut) needs every blend to keep
+    pixel values inside 0..255: true for alpha and colours in [0, 1] (what display_instances
+    passes); anything else takes the per-pixel float64 form."""
+    oma = 1 - alpha
+    return bool(oma >= 0 and tab.size > 0 and float(tab.min()) >= 0 and
+                255 * oma + float(tab.max()) < 256)
+
+
 def _is_triple(x):
     return len(x) == 3 and not hasattr(x[0], "__len__")
 
 
-def composite_batch(engine, images, colors, alpha=0.5, stream=None):
+def composite_batch(engine, images, colors, alpha=0.5, stream=None, table=None):
     """Overlay the masks an `UnmoldEngine` holds on its device canvas (after `enqueue`).
 
     images: list of uint8 HxWx3 arrays (NumPy or CUDA tensors), one per planned image, each
     of the engine's canvas size for that image.  colors: a list of RGB triples shared by all
     images, or one such list per image.  Returns a list of uint8 HxWx3 CUDA tensors.
+    table: None = tabulate the blend when that is exact (alpha, colours in [0, 1]), else
+    evaluate it per pixel in float64; False forces the per-pixel form (same output).
     """
     import torch
 
@@ -83,11 +94,13 @@ def composite_batch(engine, images, colors, alpha=0.5, stream=None):
     d_tab = torch.from_numpy(tab).to(dev)
     d_off = torch.from_numpy(offs[:B].copy()).to(dev)
     max_px = max(int(geom[b][0]) * int(geom[b][1]) for b in range(B))
+    d_lut = torch.empty((B * engine.R * 768,), dtype=torch.uint8, device=dev) \
+        if (table is None and _table_is_valid(tab, alpha)) or table else None
     N.check(lib.mrx_composite_masks(
         _ptr(engine.d_canvas), _ptr(engine.d_canvas_off), _ptr(engine.d_counts),
         _ptr(engine.d_geom), _ptr(engine.d_boxes), _ptr(d_in), _ptr(d_off), _ptr(d_tab),
-        C.c_double(1 - alpha), _ptr(d_out), B, engine.R, C.c_longlong(max_px),
-        N.stream_ptr(stream)), "mrx_composite_masks")
+        C.c_double(1 - alpha), _ptr(d_lut) if d_lut is not None else C.c_void_p(0), _ptr(d_out),
+        B, engine.R, C.c_longlong(max_px), N.stream_ptr(stream)), "mrx_composite_masks")
     return [d_out[int(offs[b]):int(offs[b + 1])].view(int(geom[b][0]), int(geom[b][1]), 3)
             for b in range(B)]
 
@@ -120,10 +133,14 @@ def apply_masks(image, boxes, masks, colors, alpha=0.5):
     d_boxes = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.int32)).to(dev)
     d_img = torch.from_numpy(image.astype(np.uint8, copy=False)).to(dev)
     d_out = torch.empty_like(d_img)
-    d_tab = torch.from_numpy(blend_table(colors, alpha, n)).to(dev)
+    tab = blend_table(colors, alpha, n)
+    d_tab = torch.from_numpy(tab).to(dev)
+    d_lut = torch.empty((n * 768,), dtype=torch.uint8, device=dev) \
+        if _table_is_valid(tab, alpha) else None
     N.check(lib.mrx_composite_masks(
         _ptr(d_canvas), _ptr(d_off), _ptr(d_counts), _ptr(d_geom), _ptr(d_boxes), _ptr(d_img),
-        _ptr(d_off), _ptr(d_tab), C.c_double(1 - alpha), _ptr(d_out), 1, n,
+        _ptr(d_off), _ptr(d_tab), C.c_double(1 - alpha),
+        _ptr(d_lut) if d_lut is not None else C.c_void_p(0), _ptr(d_out), 1, n,
         C.c_longlong(H * W), N.stream_ptr(None)), "mrx_composite_masks")
     return d_out.cpu().numpy()
 

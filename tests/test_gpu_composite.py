@@ -86,3 +86,43 @@ def test_unmold_overlay_batch(cuda_device):
         rb, rc, rs, rm = api_utils.unmold_detections(*item_of(im, np.float32))
         assert np.array_equal(b, rb) and np.array_equal(c, rc) and np.array_equal(s, rs)
         assert np.array_equal(overlay, oracle.composite_instances(image, rb, rm, colors))
+
+
+def test_tabulated_and_per_pixel_blend_agree(cuda_device):
+    """The blend is evaluated either per (pixel, instance) in float64 or once per (instance,
+    channel, value) into a table (when alpha and the colours keep values in 0..255): same bytes."""
+    import torch
+
+    rng = np.random.default_rng(45)
+    hw = (256, 320)
+    ims = synth.make_batch(45, 2, hw, 40, num_classes=6, max_instances=40)
+    eng = UnmoldEngine(2, 40, (28, 28), 6)
+    eng.plan([make_geom(im.original_image_shape, im.image_shape, im.window) for im in ims])
+    d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
+    d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
+    eng.enqueue(d_det, d_msk)
+    images = [synth.synth_rgb_image(rng, *hw) for _ in ims]
+    colors = visualize.random_colors(40, rng=random.Random(11))
+    for alpha in (0.5, 0.3, 1.0, 0.0):
+        a = visualize.composite_batch(eng, images, colors, alpha, table=None)
+        b = visualize.composite_batch(eng, images, colors, alpha, table=False)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    counts, boxes, _, _ = eng.fetch_meta()
+    masks = eng.canvas_view(0, int(counts[0])).cpu().numpy().view(np.bool_)
+    ref = oracle.composite_instances(images[0], boxes[0, :int(counts[0])], masks, colors, 0.3)
+    assert np.array_equal(visualize.composite_batch(eng, images, colors, 0.3)[0].cpu().numpy(), ref)
+
+
+def test_out_of_range_colours_take_the_exact_form(cuda_device):
+    """Colours above 1 push values past 255 (uint32 working copy, wrapped by the final uint8
+    cast): not tabulable; the per-pixel float64 form must still match the oracle."""
+    rng = np.random.default_rng(46)
+    hw = (90, 120)
+    im = synth.make_batch(46, 1, hw, 15, num_classes=3, max_instances=16)[0]
+    boxes, _, _, masks = api_utils.unmold_detections(*item_of(im))
+    image = synth.synth_rgb_image(rng, *hw)
+    colors = [(1.7, 0.2, 3.1)] * boxes.shape[0]
+    ref = oracle.composite_instances(image, boxes, masks, colors, 0.5)
+    got = visualize.apply_masks(image, boxes, masks, colors, 0.5)
+    assert np.array_equal(got, ref)
