@@ -16,6 +16,7 @@
  *   mrx_composite_masks    <- visualize.display_instances (mask overlay)  serve.py:160-169
  *   mrx_pack_masks         (extension: bit-packed transport of the masks of serve.py:147)
  *   mrx_mask_expand_packed (extension: the expand step writing that packed layout directly)
+ *   mrx_rle_count / _write (extension: the same masks as COCO run-length encodings)
  *   mrx_peer_*             (multi-GPU: the final gather of the masks to rank 0)
  *
  * Conventions
@@ -208,13 +209,16 @@ int mrx_mold_image_batch(const unsigned char *d_src, int B, int src_h, int src_w
  *   the blend -- the same float64 expression, once per (image, instance, channel, value 0..255)
  *   -- and the per-pixel walk looks it up; identical output, but ONLY valid when every blend
  *   keeps values in 0..255, i.e. one_minus_alpha >= 0, every d_blend entry >= 0 and
- *   255 * one_minus_alpha + max(d_blend) < 256 (alpha and colours in [0,1]); the caller checks. */
+ *   255 * one_minus_alpha + max(d_blend) < 256 (alpha and colours in [0,1]); the caller checks.
+ *   masks_in_boxes: non-zero promises that instance i is zero outside d_boxes[b][i] (true for a
+ *   canvas written by mrx_mask_expand): each block of pixels then visits only the instances
+ *   whose box meets it.  0: every instance byte of every pixel is examined (arbitrary masks). */
 int mrx_composite_masks(const unsigned char *d_canvas, const long long *d_canvas_off,
                         const int *d_counts, const int *d_geom, const int *d_boxes,
                         const unsigned char *d_images, const long long *d_image_off,
                         const double *d_blend, double one_minus_alpha,
-                        unsigned char *d_lut, unsigned char *d_out, int B, int R,
-                        long long max_pixels, void *stream);
+                        unsigned char *d_lut, int masks_in_boxes, unsigned char *d_out,
+                        int B, int R, long long max_pixels, void *stream);
 
 /* ---------------------------------------------------------------- packed masks (8f) */
 /* EXTENSION (not the reference layout): bit-packed copy of the canvases for transport.
@@ -242,6 +246,25 @@ int mrx_mask_expand_packed(const float *d_tiles, const int *d_tile_index, const 
                            const int *d_geom, const long long *d_packed_off,
                            unsigned char *d_packed, int B, int R, int mh, int mw, int max_w,
                            unsigned int *d_sched, void *stream);
+
+/* EXTENSION: COCO run-length masks (pycocotools' "uncompressed RLE": the mask in COLUMN-major
+ * order as alternating run lengths of zeros and ones, starting with zeros), computed from the
+ * tiles with the arithmetic of mrx_mask_expand -- decoding them gives that kernel's masks bit
+ * for bit -- without materialising any mask (rle.cu).  Two calls around one host read:
+ *   mrx_rle_count:  d_col_count [B,R,max_w] int32 scratch; d_inst_off [B*R+1] int64: on return
+ *                   (stream-ordered) d_inst_off[i] = number of value changes of all instances
+ *                   before i = b*R + k, d_inst_off[B*R] = their total T.  The caller reads T and
+ *                   allocates d_positions [T] and d_run_lengths [T + B*R] (uint32).
+ *   mrx_rle_write:  instance i's runs are d_run_lengths[d_inst_off[i] + i ...], one more than
+ *                   its value changes (d_inst_off[i+1] - d_inst_off[i] + 1); they sum to H*W.
+ * Inputs as for mrx_mask_expand_packed.  Mask tiles wider than 30 columns: MRX_E_UNSUPPORTED. */
+int mrx_rle_count(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
+                  const int *d_counts, const int *d_geom, int *d_col_count,
+                  long long *d_inst_off, int B, int R, int mh, int mw, int max_w, void *stream);
+int mrx_rle_write(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
+                  const int *d_counts, const int *d_geom, int *d_col_count,
+                  long long *d_inst_off, unsigned int *d_positions, unsigned int *d_run_lengths,
+                  int B, int R, int mh, int mw, int max_w, void *stream);
 
 /* ---------------------------------------------------------------- multi-GPU gather (8e) */
 /* Peer-memory plumbing for the final gather of the canvases to rank 0 (one process per GPU).

@@ -53,6 +53,8 @@ SIGNATURES = {
                                     _vp, _vp]),
     "mrx_mask_expand_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp,
                                     _vp]),
+    "mrx_rle_count": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "mrx_rle_write": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "mrx_peer_alloc": (_i, [C.c_ulonglong, C.POINTER(C.c_void_p)]),
     "mrx_peer_free": (_i, [_vp]),
     "mrx_peer_export": (_i, [_vp, C.c_char_p]),
@@ -65,8 +67,8 @@ SIGNATURES = {
     "mrx_cv2_resize_u8c3_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "mrx_mold_image_batch": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, _i, _vp, _vp,
                                   _vp]),
-    "mrx_composite_masks": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _i,
-                                 _i, C.c_longlong, _vp]),
+    "mrx_composite_masks": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, _i, _vp,
+                                 _i, _i, C.c_longlong, _vp]),
     "mrx_pack_masks": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 

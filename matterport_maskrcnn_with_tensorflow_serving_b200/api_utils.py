@@ -9,7 +9,7 @@ NumPy value semantics, computed by the sm_100a kernels in libmrx.so.
 
 Plus batched entry points the reference lacks (it is hard-wired to one image per call,
 serve.py:48): `unmold_detections_batch`, `unmold_detections_packed_batch`,
-`unmold_overlay_batch`.
+`unmold_detections_rle_batch`, `unmold_overlay_batch`.
 
 Numerical contract (checked by tests/ against the float64 oracle): N, boxes, class ids and
 scores are bit-exact.  The mask resize runs in float32 on exact integer source coordinates;
@@ -334,6 +334,33 @@ def unmold_detections_packed_batch(items, direct=True):
         wb = (W + 7) // 8
         pk = np.empty((0, H, wb), np.uint8) if k == 0 else arrays[b].reshape(k, H, wb)
         out.append(metas[b] + (pk,))
+    return out
+
+
+def unmold_detections_rle_batch(items):
+    """EXTENSION (not the reference layout): like `unmold_detections_batch` but every mask comes
+    back as a COCO run-length encoding -- pycocotools' "uncompressed RLE" dict
+    {'size': [H, W], 'counts': uint32 array} (column-major runs starting with zeros) -- computed
+    on the device straight from the 28x28 tiles; the [H,W,N] masks are never materialised and
+    only the run lengths (a few KB per mask) travel to the host.  Decoding a result gives exactly
+    the mask `unmold_detections` returns.  Returns a list of (boxes, class_ids, scores, rles)."""
+    if len(items) == 0:
+        return []
+    with _Staged(items, canvas=False) as st:
+        eng = st.eng
+        eng.enqueue(st.d_det, st.d_msk, expand=False)
+        d_runs, off = eng.enqueue_rle()
+        counts, metas = st.meta()
+        runs = d_runs.cpu().numpy().view(np.uint32)
+    out = []
+    for b in range(st.n):
+        H, W = int(st.geoms[b][0]), int(st.geoms[b][1])
+        rles = []
+        for k in range(int(counts[b])):
+            i = b * eng.R + k
+            rles.append({"size": [H, W],
+                         "counts": runs[int(off[i]) + i:int(off[i + 1]) + i + 1].copy()})
+        out.append(metas[b] + (rles,))
     return out
 
 

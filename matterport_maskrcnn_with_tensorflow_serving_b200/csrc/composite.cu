@@ -46,7 +46,10 @@ composite_lut_kernel(const int *__restrict__ counts, const int4 *__restrict__ bo
   }
 }
 
-template <bool kLut>
+// kCull: the canvas was written by mrx_mask_expand, so instance i is zero outside its box: the
+// CTA first lists (in order) the instances whose box meets its pixels -- about ten of a hundred
+// -- and every pixel then looks at those bytes only, instead of walking all N.
+template <bool kLut, bool kCull>
 __global__ void __launch_bounds__(kCompThreads)
 composite_masks_kernel(const unsigned char *__restrict__ canvas,
                        const long long *__restrict__ canvas_off,
@@ -70,6 +73,11 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   unsigned char *s_skip = smem + ((static_cast<size_t>(R) * 3 * sizeof(double) + 15) & ~static_cast<size_t>(15));
   unsigned char *s_can = s_skip + ((R + 15) & ~15);
 
+  __shared__ int s_wcnt[kCompThreads / 32];
+  __shared__ int s_nlist;
+  // the candidate list reuses the skip-flag bytes as 16-bit entries when R is small enough
+  // for them to fit (R + 15 bytes hold R/2 entries): it has its own array instead
+  unsigned short *s_list = reinterpret_cast<unsigned short *>(s_can + ((static_cast<size_t>(kCompThreads) * R + 31) & ~static_cast<size_t>(15)));
   if (!kLut) {
     for (int i = t; i < N * 3; i += kCompThreads)
       s_blend[i] = blend[static_cast<size_t>(b) * R * 3 + i];
@@ -77,6 +85,35 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
       const int4 bx = boxes[static_cast<size_t>(b) * R + i];
       s_skip[i] = (bx.x | bx.y | bx.z | bx.w) == 0;   // upstream: `if not np.any(boxes[i]): continue`
     }
+  }
+  if (kCull) {
+    // rows / columns the CTA's pixels span (a run of consecutive pixels in row-major order)
+    const int ya = static_cast<int>(p0 / W), yb = static_cast<int>((p0 + npx - 1) / W);
+    const int xa = ya == yb ? static_cast<int>(p0 - static_cast<long long>(ya) * W) : 0;
+    const int xb = ya == yb ? xa + npx : W;   // exclusive
+    int running = 0;
+    for (int base = 0; base < N; base += kCompThreads) {
+      const int i = base + t;
+      bool hit = false;
+      if (i < N) {
+        const int4 bx = boxes[static_cast<size_t>(b) * R + i];   // (y1, x1, y2, x2)
+        hit = bx.x <= yb && bx.z > ya && bx.y < xb && bx.w > xa;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if ((t & 31) == 0) s_wcnt[t >> 5] = __popc(bal);
+      __syncthreads();
+      int before = running, total = 0;
+#pragma unroll
+      for (int w = 0; w < kCompThreads / 32; ++w) {
+        const int c = s_wcnt[w];
+        if (w < (t >> 5)) before += c;
+        total += c;
+      }
+      if (hit) s_list[before + __popc(bal & ((1u << (t & 31)) - 1u))] = static_cast<unsigned short>(i);
+      running += total;
+      __syncthreads();
+    }
+    if (t == 0) s_nlist = running;
   }
   if (N > 0) {
     // 256*N is a multiple of 16 and so is every canvas slot offset: whole uint4 loads; the
@@ -118,7 +155,13 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
     v2 = __double2uint_rz(__dadd_rn(__dmul_rn(static_cast<double>(v2), one_minus_alpha), bl[2]));
   };
   const unsigned char *mp = s_can + static_cast<size_t>(t) * N;
-  if ((N & 3) == 0) {
+  if (kCull) {
+    const int nl = s_nlist;
+    for (int c = 0; c < nl; ++c) {   // instance order is preserved by the compaction
+      const int i = s_list[c];
+      if (mp[i]) apply(i);
+    }
+  } else if ((N & 3) == 0) {
     // ~3 % of the bytes are set: test five words (20 instances) with one OR before looking
     // at any of them
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mp);
@@ -157,8 +200,9 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
                                    const int *d_counts, const int *d_geom, const int *d_boxes,
                                    const unsigned char *d_images, const long long *d_image_off,
                                    const double *d_blend, double one_minus_alpha,
-                                   unsigned char *d_lut, unsigned char *d_out, int B, int R,
-                                   long long max_pixels, void *stream) {
+                                   unsigned char *d_lut, int masks_in_boxes,
+                                   unsigned char *d_out, int B, int R, long long max_pixels,
+                                   void *stream) {
   using namespace mrx;
   MRX_CHECK_ARG(d_canvas && d_canvas_off && d_counts && d_geom && d_boxes && d_images &&
                     d_image_off && d_blend && d_out,
@@ -170,7 +214,8 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
   if (int rc = current_device_info(&dev)) return rc;
   const int max_optin = dev.max_smem_optin;
   const size_t smem = ((static_cast<size_t>(R) * 3 * sizeof(double) + 15) & ~static_cast<size_t>(15)) +
-                      ((R + 15) & ~15) + static_cast<size_t>(kCompThreads) * R + 16;
+                      ((R + 15) & ~15) + static_cast<size_t>(kCompThreads) * R + 32 +
+                      static_cast<size_t>(R) * sizeof(unsigned short) + 16;
   MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(max_optin),
                       "mrx_composite_masks: R=%d needs %zu B of shared memory (limit %d)", R, smem,
                       max_optin);
@@ -182,22 +227,22 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
   if (d_lut != nullptr) {
     composite_lut_kernel<<<dim3(R, B), 256, 0, st>>>(d_counts, boxes4, d_blend, one_minus_alpha, d_lut, R);
     MRX_LAUNCH_CHECK("composite_lut_kernel");
-    static SmemCache cache;
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(composite_masks_kernel<true>), &cache,
-                                     dev.device, static_cast<int>(smem)))
-      return rc;
-    composite_masks_kernel<true><<<grid, kCompThreads, smem, st>>>(
-        d_canvas, d_canvas_off, d_counts, d_geom, boxes4, d_images, d_image_off, d_blend,
-        one_minus_alpha, d_lut, d_out, R);
-  } else {
-    static SmemCache cache;
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(composite_masks_kernel<false>), &cache,
-                                     dev.device, static_cast<int>(smem)))
-      return rc;
-    composite_masks_kernel<false><<<grid, kCompThreads, smem, st>>>(
-        d_canvas, d_canvas_off, d_counts, d_geom, boxes4, d_images, d_image_off, d_blend,
-        one_minus_alpha, nullptr, d_out, R);
   }
+#define MRX_COMPOSITE(LUT, CULL)                                                                   \
+  do {                                                                                             \
+    static SmemCache cache;                                                                        \
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(composite_masks_kernel<LUT, CULL>), \
+                                     &cache, dev.device, static_cast<int>(smem)))                  \
+      return rc;                                                                                   \
+    composite_masks_kernel<LUT, CULL><<<grid, kCompThreads, smem, st>>>(                           \
+        d_canvas, d_canvas_off, d_counts, d_geom, boxes4, d_images, d_image_off, d_blend,          \
+        one_minus_alpha, d_lut, d_out, R);                                                         \
+  } while (0)
+  if (d_lut != nullptr && masks_in_boxes) MRX_COMPOSITE(true, true);
+  else if (d_lut != nullptr) MRX_COMPOSITE(true, false);
+  else if (masks_in_boxes) MRX_COMPOSITE(false, true);
+  else MRX_COMPOSITE(false, false);
+#undef MRX_COMPOSITE
   MRX_LAUNCH_CHECK("composite_masks_kernel");
   return MRX_OK;
 }

@@ -30,6 +30,8 @@
 // columns) plus 1/8 of the canvas bytes to HBM; see DESIGN.md 3.9 for the measured figures.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "expand.cuh"
 
 #ifndef MRX_BITS_WARPS_DEFAULT
@@ -219,7 +221,7 @@ mask_expand_bits_kernel(const BitsParams p) {
       for (int cb0 = bx.y >> 5; cb0 <= cb_last; cb0 += kGroup) {
         int idx[kGroup];
         float wx[kGroup], thr[kGroup], ht[kGroup], hb[kGroup], dh[kGroup];
-        int nbytes[kGroup];
+        bool store[kGroup];    // this lane stores (a byte of) block c's ballot
 #pragma unroll
         for (int c = 0; c < kGroup; ++c) {
           const int cb = cb0 + c;
@@ -240,7 +242,10 @@ mask_expand_bits_kernel(const BitsParams p) {
           idx[c] = min(max(i0 + 1, 0), 30);
           wx[c] = static_cast<float>(rem) * invD;
           thr[c] = colvalid ? 0.5f : __int_as_float(0x7f800000);
-          nbytes[c] = cb <= cb_last ? min(4, WB - (cb << 2)) : 0;   // bytes of the block inside the row
+          // bytes of the block inside the row: lane 0 stores the word when rows are 4-byte
+          // aligned (then all four are inside), else lane t < nbytes stores byte t
+          const int nbytes = cb <= cb_last ? min(4, WB - (cb << 2)) : 0;
+          store[c] = word_ok ? (lane == 0 && nbytes > 0) : (lane < nbytes);
         }
         auto hrow = [&](float rv, int c) -> float {
           const float lo = __shfl_sync(0xffffffffu, rv, idx[c]);
@@ -259,47 +264,52 @@ mask_expand_bits_kernel(const BitsParams p) {
         }
         float rawn = raw(jcur + 2);   // fetched one advance ahead
         uint32_t addr = row0_addr + static_cast<uint32_t>(cb0 << 2);
-        for (int r = ya; r < yb; ++r) {
-          if (j0 != jcur) {   // warp-uniform
-            if (j0 == jcur + 1) {
+        // the row loop, once per store form so that the form is not re-decided per row
+        auto rows = [&](auto word_tag) {
+          constexpr bool kWord = decltype(word_tag)::value;
+          const uint32_t sh = kWord ? 0u : 8u * lane;          // byte t of the ballot for lane t
+          for (int r = ya; r < yb; ++r) {
+            if (j0 != jcur) {   // warp-uniform
+              if (j0 == jcur + 1) {
 #pragma unroll
-              for (int c = 0; c < kGroup; ++c) {
-                ht[c] = hb[c];
-                hb[c] = hrow(rawn, c);
+                for (int c = 0; c < kGroup; ++c) {
+                  ht[c] = hb[c];
+                  hb[c] = hrow(rawn, c);
+                }
+              } else {
+                const float ra = raw(j0), rbv = raw(j0 + 1);
+#pragma unroll
+                for (int c = 0; c < kGroup; ++c) {
+                  ht[c] = hrow(ra, c);
+                  hb[c] = hrow(rbv, c);
+                }
               }
-            } else {
-              const float ra = raw(j0), rbv = raw(j0 + 1);
+              jcur = j0;
+              rawn = raw(jcur + 2);
 #pragma unroll
-              for (int c = 0; c < kGroup; ++c) {
-                ht[c] = hrow(ra, c);
-                hb[c] = hrow(rbv, c);
+              for (int c = 0; c < kGroup; ++c) dh[c] = hb[c] - ht[c];
+            }
+            const float wy = static_cast<float>(remy) * invDy;
+#pragma unroll
+            for (int c = 0; c < kGroup; ++c) {
+              const float v = fmaf(wy, dh[c], ht[c]);
+              const unsigned bal = __ballot_sync(0xffffffffu, v >= thr[c]);
+              if (store[c]) {
+                if (kWord) asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr + 4u * c), "r"(bal));
+                else asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + 4u * c + lane), "r"(bal >> sh));
               }
             }
-            jcur = j0;
-            rawn = raw(jcur + 2);
-#pragma unroll
-            for (int c = 0; c < kGroup; ++c) dh[c] = hb[c] - ht[c];
-          }
-          const float wy = static_cast<float>(remy) * invDy;
-#pragma unroll
-          for (int c = 0; c < kGroup; ++c) {
-            const float v = fmaf(wy, dh[c], ht[c]);
-            const unsigned bal = __ballot_sync(0xffffffffu, v >= thr[c]);
-            const uint32_t ac = addr + 4u * c;
-            if (word_ok) {   // WB % 4 == 0: all four bytes of a block are inside the row
-              if (lane == 0 && nbytes[c] > 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ac), "r"(bal));
-            } else if (lane < nbytes[c]) {
-              asm volatile("st.shared.u8 [%0], %1;" ::"r"(ac + lane), "r"(bal >> (8 * lane)));
+            addr += static_cast<uint32_t>(WB);
+            remy += stepRy;
+            j0 += stepQy;
+            if (remy >= Dy) {
+              remy -= Dy;
+              ++j0;
             }
           }
-          addr += static_cast<uint32_t>(WB);
-          remy += stepRy;
-          j0 += stepQy;
-          if (remy >= Dy) {
-            remy -= Dy;
-            ++j0;
-          }
-        }
+        };
+        if (word_ok) rows(std::true_type{});
+        else rows(std::false_type{});
       }
       fence_proxy_async_smem();   // this lane's bytes -> visible to the bulk copy
       __syncwarp();

@@ -54,18 +54,34 @@ pack_quads_kernel(const unsigned char *__restrict__ canvas, const long long *__r
   const uint32_t *src = reinterpret_cast<const uint32_t *>(
                             canvas + canvas_off[b] + (static_cast<long long>(y) * W + x0) * N) + q;
   uint32_t acc[4];
+  const unsigned stride = static_cast<unsigned>(nquads);   // words per pixel (32-bit index math)
+  const unsigned stride_bytes = static_cast<unsigned>(N);
+  const unsigned char *srcb = reinterpret_cast<const unsigned char *>(src);
+  if (npx == 32) {
+    // whole run inside the row (always, when W % 32 == 0): 32 unpredicated loads
 #pragma unroll
-  for (int bq = 0; bq < 4; ++bq) {
-    uint32_t w[8];
+    for (int bq = 0; bq < 4; ++bq) {
+      uint32_t w[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int px = 8 * bq + k;
-      w[k] = px < npx ? __ldg(src + static_cast<size_t>(px) * nquads) : 0u;
+      for (int k = 0; k < 8; ++k)   // one 32x32+64 multiply-add per address
+        w[k] = __ldg(reinterpret_cast<const uint32_t *>(
+            srcb + static_cast<unsigned long long>(8 * bq + k) * static_cast<unsigned long long>(stride_bytes)));
+      uint32_t a = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a |= (w[k] & 0x01010101u) << (7 - k);
+      acc[bq] = a;
     }
-    uint32_t a = 0u;
+  } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a |= (w[k] & 0x01010101u) << (7 - k);
-    acc[bq] = a;
+    for (int bq = 0; bq < 4; ++bq) {
+      uint32_t a = 0u;
+      for (int k = 0; k < 8; ++k) {
+        const int px = 8 * bq + k;
+        const uint32_t w = px < npx ? __ldg(src + static_cast<unsigned>(px) * stride) : 0u;
+        a |= (w & 0x01010101u) << (7 - k);
+      }
+      acc[bq] = a;
+    }
   }
   // acc[bq] byte j = packed byte bq of instance 4q + j  ->  word of instance j = bytes 0..3
   const uint32_t t0 = __byte_perm(acc[0], acc[1], 0x5140), t1 = __byte_perm(acc[2], acc[3], 0x5140);

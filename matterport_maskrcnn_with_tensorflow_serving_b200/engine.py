@@ -283,6 +283,31 @@ class UnmoldEngine:
         o = int(self._offsets[b])
         return self.d_canvas[o:o + H * W * n_kept].view(H, W, n_kept)
 
+    def enqueue_rle(self, stream=None):
+        """EXTENSION: COCO run-length encodings of the planned batch's masks, from the tiles
+        (after `enqueue(..., expand=False)`; no mask is materialised).  Synchronises once to
+        size the output.  Returns (d_run_lengths uint32 tensor, inst_off int64 ndarray [n*R+1]):
+        instance i = b*R + k owns d_run_lengths[inst_off[i] + i : inst_off[i+1] + i + 1]."""
+        torch = _torch()
+        n = self._n_images
+        g = self._geom_host
+        max_w = int(g[:, 1].max())
+        dev = self.device
+        d_col = torch.empty((n * self.R * max_w,), dtype=torch.int32, device=dev)
+        d_off = torch.empty((n * self.R + 1,), dtype=torch.int64, device=dev)
+        st = N.stream_ptr(stream)
+        args = (_ptr(self.d_tiles), _ptr(self.d_src_index), _ptr(self.d_boxes), _ptr(self.d_counts),
+                _ptr(self.d_geom), _ptr(d_col), _ptr(d_off))
+        N.check(self.lib.mrx_rle_count(*args, n, self.R, self.mh, self.mw, max_w, st),
+                "mrx_rle_count")
+        off = d_off.cpu().numpy()          # the one synchronisation: how many runs there are
+        total = int(off[-1])
+        d_pos = torch.empty((max(total, 1),), dtype=torch.int32, device=dev)
+        d_runs = torch.empty((total + n * self.R,), dtype=torch.int32, device=dev)
+        N.check(self.lib.mrx_rle_write(*args, _ptr(d_pos), _ptr(d_runs), n, self.R, self.mh,
+                                       self.mw, max_w, st), "mrx_rle_write")
+        return d_runs, off
+
     def pack_masks(self, stream=None):
         """EXTENSION: bit-pack the byte canvases already written for the planned batch
         (mrx_pack_masks; same output layout as `enqueue_expand_packed`).  Returns

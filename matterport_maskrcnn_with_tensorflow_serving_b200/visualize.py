@@ -58,7 +58,7 @@ def _is_triple(x):
     return len(x) == 3 and not hasattr(x[0], "__len__")
 
 
-def composite_batch(engine, images, colors, alpha=0.5, stream=None, table=None):
+def composite_batch(engine, images, colors, alpha=0.5, stream=None, table=None, cull=True):
     """Overlay the masks an `UnmoldEngine` holds on its device canvas (after `enqueue`).
 
     images: list of uint8 HxWx3 arrays (NumPy or CUDA tensors), one per planned image, each
@@ -66,6 +66,8 @@ def composite_batch(engine, images, colors, alpha=0.5, stream=None, table=None):
     images, or one such list per image.  Returns a list of uint8 HxWx3 CUDA tensors.
     table: None = tabulate the blend when that is exact (alpha, colours in [0, 1]), else
     evaluate it per pixel in float64; False forces the per-pixel form (same output).
+    cull: visit, per block of pixels, only the instances whose box meets it (valid because the
+    expand kernel never sets a pixel outside the box; False walks every instance -- same output).
     """
     import torch
 
@@ -99,8 +101,10 @@ def composite_batch(engine, images, colors, alpha=0.5, stream=None, table=None):
     N.check(lib.mrx_composite_masks(
         _ptr(engine.d_canvas), _ptr(engine.d_canvas_off), _ptr(engine.d_counts),
         _ptr(engine.d_geom), _ptr(engine.d_boxes), _ptr(d_in), _ptr(d_off), _ptr(d_tab),
-        C.c_double(1 - alpha), _ptr(d_lut) if d_lut is not None else C.c_void_p(0), _ptr(d_out),
-        B, engine.R, C.c_longlong(max_px), N.stream_ptr(stream)), "mrx_composite_masks")
+        C.c_double(1 - alpha), _ptr(d_lut) if d_lut is not None else C.c_void_p(0),
+        1 if cull else 0,        # the engine's canvas: instance i is zero outside its box
+        _ptr(d_out), B, engine.R, C.c_longlong(max_px), N.stream_ptr(stream)),
+        "mrx_composite_masks")
     return [d_out[int(offs[b]):int(offs[b + 1])].view(int(geom[b][0]), int(geom[b][1]), 3)
             for b in range(B)]
 
@@ -140,8 +144,8 @@ def apply_masks(image, boxes, masks, colors, alpha=0.5):
     N.check(lib.mrx_composite_masks(
         _ptr(d_canvas), _ptr(d_off), _ptr(d_counts), _ptr(d_geom), _ptr(d_boxes), _ptr(d_img),
         _ptr(d_off), _ptr(d_tab), C.c_double(1 - alpha),
-        _ptr(d_lut) if d_lut is not None else C.c_void_p(0), _ptr(d_out), 1, n,
-        C.c_longlong(H * W), N.stream_ptr(None)), "mrx_composite_masks")
+        _ptr(d_lut) if d_lut is not None else C.c_void_p(0), 0,   # arbitrary masks: no box cull
+        _ptr(d_out), 1, n, C.c_longlong(H * W), N.stream_ptr(None)), "mrx_composite_masks")
     return d_out.cpu().numpy()
 
 

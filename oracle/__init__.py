@@ -39,4 +39,6 @@ from .mrcnn_oracle import (  # noqa: F401
     random_colors,
     apply_mask,
     composite_instances,
+    rle_encode,
+    rle_decode,
 )

@@ -398,3 +398,31 @@ def composite_instances(image, boxes, masks, colors, alpha=0.5):
             continue
         masked_image = apply_mask(masked_image, masks[:, :, i], colors[i], alpha)
     return masked_image.astype(np.uint8)
+
+
+# =====================================================================================
+# COCO run-length encoding of a mask  -- SURVEY.md 8f rank 4 (compact mask formats)
+# =====================================================================================
+def rle_encode(mask):
+    """[PUBLISHED FORMAT, pycocotools maskApi.c rleEncode] "uncompressed RLE" of one binary
+    mask [H, W]: the pixels in COLUMN-major (Fortran) order as alternating run lengths of zeros
+    and ones, starting with zeros (so the list starts with 0 when the first pixel is set).
+    Returns {'size': [H, W], 'counts': uint32 ndarray}.  pycocotools itself is not installed
+    here; this is the definition its `frPyObjects` accepts and its `decode` inverts."""
+    mask = np.asarray(mask)
+    h, w = mask.shape
+    flat = mask.reshape(-1, order="F").astype(np.uint8)
+    change = np.flatnonzero(np.diff(np.concatenate([[0], flat]))) if flat.size else np.array([], np.int64)
+    edges = np.concatenate([[0], change, [flat.size]])
+    return {"size": [int(h), int(w)], "counts": np.diff(edges).astype(np.uint32)}
+
+
+def rle_decode(rle):
+    """Inverse of rle_encode: bool [H, W]."""
+    h, w = rle["size"]
+    counts = np.asarray(rle["counts"], dtype=np.int64)
+    vals = np.zeros(len(counts), dtype=np.uint8)
+    vals[1::2] = 1
+    flat = np.repeat(vals, counts)
+    assert flat.size == h * w, (flat.size, h, w)
+    return flat.reshape((h, w), order="F").astype(np.bool_)

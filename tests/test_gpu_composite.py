@@ -106,8 +106,12 @@ def test_tabulated_and_per_pixel_blend_agree(cuda_device):
     for alpha in (0.5, 0.3, 1.0, 0.0):
         a = visualize.composite_batch(eng, images, colors, alpha, table=None)
         b = visualize.composite_batch(eng, images, colors, alpha, table=False)
-        for x, y in zip(a, b):
-            assert torch.equal(x, y)
+        # ... and with / without restricting every block of pixels to the instances whose box
+        # meets it (the expand kernel never sets a pixel outside the box)
+        c = visualize.composite_batch(eng, images, colors, alpha, table=None, cull=False)
+        d = visualize.composite_batch(eng, images, colors, alpha, table=False, cull=False)
+        for x, y, z, w in zip(a, b, c, d):
+            assert torch.equal(x, y) and torch.equal(x, z) and torch.equal(x, w)
     counts, boxes, _, _ = eng.fetch_meta()
     masks = eng.canvas_view(0, int(counts[0])).cpu().numpy().view(np.bool_)
     ref = oracle.composite_instances(images[0], boxes[0, :int(counts[0])], masks, colors, 0.3)
