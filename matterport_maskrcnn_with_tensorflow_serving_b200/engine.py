@@ -130,8 +130,10 @@ class UnmoldEngine:
         if n < 1 or n > self.B:
             raise ValueError(f"batch of {n} images does not fit max_batch={self.B}")
         if self._geom_host is not None and self._geom_host.shape == g.shape and \
-                np.array_equal(self._geom_host, g) and (self.d_canvas is not None or not canvas):
-            return
+                np.array_equal(self._geom_host, g) and \
+                (not canvas or (self.d_canvas is not None and
+                                self.d_canvas.numel() >= int(self._offsets[-1]))):
+            return      # (a plan made with canvas=False may have left a smaller canvas behind)
         if (g[:, :4] < 2).any():
             raise ValueError("image sides must be >= 2")
         if (g[:, 0].astype(np.int64) * g[:, 1] > (1 << 30)).any():

@@ -85,3 +85,15 @@ def test_expand_packed_equals_byte_canvas_on_device(cuda_device, hw, n, R, batch
             plane = torch.nn.functional.pad(plane, (0, pad))
         ref = (plane.view(H, wb, 8) * weights).sum(-1).to(torch.uint8)
         assert torch.equal(a.view(k, H, wb)[i], ref)
+
+
+def test_byte_canvas_after_a_canvasless_plan(cuda_device):
+    """Regression: a packed / RLE call plans a new geometry without a byte canvas; the next
+    byte-canvas call on the same cached engine must size the canvas for THAT geometry."""
+    small = synth.make_batch(64, 1, (40, 56), 5, num_classes=4, max_instances=8)[0]
+    big = synth.make_batch(65, 1, (300, 260), 8, num_classes=4, max_instances=8)[0]
+    api_utils.unmold_detections(*item_of(small, np.float32))          # small canvas cached
+    (pb, pc, ps, packed), = api_utils.unmold_detections_packed_batch([item_of(big, np.float32)])
+    b, c, s, m = api_utils.unmold_detections(*item_of(big, np.float32))
+    assert m.shape == (300, 260, b.shape[0])
+    assert np.array_equal(packed, np.packbits(m.transpose(2, 0, 1), axis=-1))
