@@ -536,11 +536,10 @@ def run_ours(args, rank, world, local_rank):
         N.check(lib.mrx_unmold_prepare(P(d_det), N.MRX_F32, P(d_msk), N.MRX_F32, BATCH, N_INST, 28,
                                        28, CLASSES, P(eng.d_geom), P(eng.d_boxes),
                                        P(eng.d_class_ids), P(eng.d_scores), P(eng.d_src_index),
-                                       P(eng.d_box_aux), P(eng.d_counts), P(eng.d_status),
+                                       P(eng.d_counts), P(eng.d_status),
                                        P(eng.d_tiles), P(eng.d_sched), st), "prepare")
         kev[s][0].record(stream)
         N.check(lib.mrx_mask_expand(P(eng.d_tiles), P(eng.d_src_index), P(eng.d_boxes),
-                                    P(eng.d_box_aux),
                                     P(eng.d_counts), P(eng.d_geom),
                                     P(eng.d_canvas_off), P(eng.d_canvas), BATCH, N_INST, 28, 28,
                                     eng.chunk_bytes, eng.ctas_per_sm, P(eng.d_sched), st),

@@ -91,17 +91,14 @@ int mrx_anchors(float *d_out, int img_h, int img_w,
  *   d_detections [B,R,6] det_dtype      d_geom [B,8] int32
  *   d_boxes [B,R,4] int32   d_class_ids [B,R] int32   d_scores [B,R] det_dtype
  *   d_src_index [B,R] int32 (kept row -> original row)
- *   d_box_aux [B,R,4] 4-byte words: per kept box the row-invariant constants of the
- *     horizontal resize coordinate for mask tiles `mw` wide (2*bw, 1/(2*bw) as float bits,
- *     (64*mw) div/mod 2*bw); consumed by mrx_mask_expand
  *   d_counts [B] int32 (N per image)    d_status [B] int32 (MRX_ST_* bits)
  * C = number of classes in mrcnn_mask's last axis (for the class-range check).
  * d_sched (may be NULL): the scheduler words of the expand kernels (MRX_SCHED_WORDS x uint32),
  * zeroed here as well. */
 int mrx_unmold_prologue(const void *d_detections, int det_dtype, int B, int R, int C,
-                        int mw, const int *d_geom,
+                        const int *d_geom,
                         int *d_boxes, int *d_class_ids, void *d_scores,
-                        int *d_src_index, int *d_box_aux, int *d_counts, int *d_status,
+                        int *d_src_index, int *d_counts, int *d_status,
                         unsigned int *d_sched, void *stream);
 
 /* masks = mrcnn_mask[src_index, :, :, class_id] packed to float32 tiles.
@@ -124,7 +121,7 @@ int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype,
 int mrx_unmold_prepare(const void *d_detections, int det_dtype, const void *d_mrcnn_mask,
                        int mask_dtype, int B, int R, int mh, int mw, int C,
                        const int *d_geom, int *d_boxes, int *d_class_ids, void *d_scores,
-                       int *d_src_index, int *d_box_aux, int *d_counts, int *d_status,
+                       int *d_src_index, int *d_counts, int *d_status,
                        float *d_tiles, unsigned int *d_sched, void *stream);
 
 /* The hot kernel.  For every image b writes the bool canvas [H_b, W_b, N_b]
@@ -143,7 +140,6 @@ int mrx_unmold_prepare(const void *d_detections, int det_dtype, const void *d_mr
  *   d_tiles[b][d_tile_index[b][k]] (NULL: d_tiles[b][k], the layout mrx_gather_tiles writes;
  *   d_src_index: the layout mrx_unmold_prepare writes).                              */
 int mrx_mask_expand(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
-                    const int *d_box_aux,
                     const int *d_counts, const int *d_geom, const long long *d_canvas_off,
                     unsigned char *d_canvas, int B, int R, int mh, int mw,
                     int chunk_bytes, int ctas_per_sm,
@@ -157,7 +153,6 @@ int mrx_mask_expand(const float *d_tiles, const int *d_tile_index, const int *d_
  * oracle (|diff| <= 1e-6).  Shapes the team kernel does not take (R > 200, mask tiles wider
  * than 30 columns) return MRX_E_UNSUPPORTED. */
 int mrx_mask_expand_values(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
-                           const int *d_box_aux,
                            const int *d_counts, const int *d_geom, const long long *d_canvas_off,
                            unsigned char *d_canvas, float *d_values, int B, int R, int mh, int mw,
                            unsigned int *d_sched, void *stream);

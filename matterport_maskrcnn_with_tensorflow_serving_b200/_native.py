@@ -42,14 +42,14 @@ SIGNATURES = {
     "mrx_device_props": (_i, [_i, _ip, _ip, _ip, _ip]),
     "mrx_anchor_count": (_i, [_i, _i, _ip, _i, _i, _i, C.POINTER(C.c_longlong)]),
     "mrx_anchors": (_i, [_vp, _i, _i, _dp, _dp, _ip, _i, _i, _i, _vp]),
-    "mrx_unmold_prologue": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp, _vp, _vp]),
+    "mrx_unmold_prologue": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp]),
     "mrx_gather_tiles": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mrx_unmold_prepare": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
-                                _vp, _vp, _vp, _vp, _vp, _vp]),
-    "mrx_mask_expand": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp,
+                                _vp, _vp, _vp, _vp, _vp]),
+    "mrx_mask_expand": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp,
                              _vp]),
-    "mrx_mask_expand_values": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+    "mrx_mask_expand_values": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
                                     _vp, _vp]),
     "mrx_mask_expand_packed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp,
                                     _vp]),

@@ -7,20 +7,10 @@
 
 namespace mrx {
 
-// Per kept box, written by unmold_prologue_kernel: the row-invariant constants of the
-// horizontal source coordinate  src = (mw*(2*(x-x1)+1) - bw) / (2*bw).
-struct __align__(16) BoxAux {
-  int D;        // 2 * box width; 0 marks a box the expand kernels must skip (outside the canvas)
-  float invD;   // 1 / D
-  int stepQ;    // (64*mw) / D : source-column advance per 32 canvas columns
-  int stepR;    // (64*mw) % D
-};
-
 struct ExpandParams {
   const float *tiles;           // [B,R,mh,mw]
   const int *tile_index;        // [B,R] tile of kept instance k = tiles[b][tile_index[b][k]]; NULL: k
   const int4 *boxes;            // [B,R] (y1,x1,y2,x2)
-  const BoxAux *aux;            // [B,R]
   const int *counts;            // [B]
   const int *geom;              // [B,8]
   const long long *canvas_off;  // [B]

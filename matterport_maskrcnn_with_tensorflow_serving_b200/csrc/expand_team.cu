@@ -83,7 +83,8 @@ struct __align__(16) TJob {
   int y0, kk;          // first row and number of rows
   int pitch;           // shared-memory distance between tile rows (multiple of 16)
   unsigned RW;         // canvas row bytes W * N
-  int pad0_, pad1_;
+  int ident;           // instance k's tile is tile k (no row was dropped): skip the index lookup
+  int pad1_;
 };
 
 // Tile geometry of an image: tile width in pixels and the shared-memory row pitch.
@@ -216,7 +217,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
   // (per-image constants live in shared memory: registers would cost every thread)
   struct DecodeCache {
     unsigned char *canvas;
-    int b, H, W, N, P, pitch, tx, pad_;
+    int b, H, W, N, P, pitch, tx, ident;
   };
   __shared__ DecodeCache s_dc[kTeams];
   DecodeCache &dc = s_dc[tm];
@@ -238,6 +239,9 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
       dc.pitch = pitch_;
       dc.tx = (dc.W + P_ - 1) / P_;
       dc.canvas = p.canvas + p.canvas_off[b];
+      // kept rows are in increasing order: no row was dropped iff the last one kept its index
+      dc.ident = p.tile_index == nullptr || dc.N == 0 ||
+                 p.tile_index[static_cast<size_t>(b) * p.R + dc.N - 1] == dc.N - 1;
     }
     const int H = dc.H, W = dc.W, N = dc.N, P = dc.P, pitch = dc.pitch, tiles_x = dc.tx;
     const int local = j - s_prefix[b];
@@ -257,6 +261,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     out->W = W;
     out->pitch = pitch;
     out->RW = RW;
+    out->ident = dc.ident;
     out->valid = 1;
   };
 
@@ -293,8 +298,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
       TEntry e;
       e.x1 = bx.y;
       e.x2 = bx.w;
-      const int tile = p.tile_index != nullptr
-                           ? __ldg(p.tile_index + (jb.boxes_b - p.boxes) + n) : n;
+      const int tile = jb.ident ? n : __ldg(p.tile_index + (jb.boxes_b - p.boxes) + n);
       e.npk = n | (tile << 8) | (ra << 16) | (rb << 22);
       e.invD = __fdiv_rn(1.0f, static_cast<float>(2 * (bx.w - bx.y)));
       e.Dy = 2 * bh;

@@ -61,8 +61,7 @@ template <typename T, int kThreads>
 __device__ __forceinline__ void prologue_body(const int b, const T *__restrict__ det, int R, int C,
                                               const int *__restrict__ geom, int *__restrict__ boxes,
                                               int *__restrict__ class_ids, T *__restrict__ scores,
-                                              int *__restrict__ src_index, BoxAux *__restrict__ aux,
-                                              int mw, int *__restrict__ counts,
+                                              int *__restrict__ src_index, int *__restrict__ counts,
                                               int *__restrict__ status,
                                               unsigned int *__restrict__ job_counter) {
   constexpr int kPrologueThreads = kThreads;   // (shadows the launch constant inside this body)
@@ -143,13 +142,6 @@ __device__ __forceinline__ void prologue_body(const int b, const T *__restrict__
       class_ids[o] = cls;
       scores[o] = score;
       src_index[o] = t;
-      // row-invariant constants of the horizontal source coordinate (D = 0: skip the box)
-      BoxAux a;
-      a.D = in_canvas ? 2 * (x2 - x1) : 0;
-      a.invD = in_canvas ? __fdiv_rn(1.0f, static_cast<float>(a.D)) : 0.f;
-      a.stepQ = in_canvas ? (64 * mw) / a.D : 0;
-      a.stepR = in_canvas ? (64 * mw) - a.stepQ * a.D : 0;
-      aux[o] = a;
     }
     running += total;
     __syncthreads();
@@ -167,11 +159,10 @@ __global__ void __launch_bounds__(kPrologueThreads)
 unmold_prologue_kernel(const T *__restrict__ det, int R, int C,
                        const int *__restrict__ geom, int *__restrict__ boxes,
                        int *__restrict__ class_ids, T *__restrict__ scores,
-                       int *__restrict__ src_index, BoxAux *__restrict__ aux, int mw,
-                       int *__restrict__ counts, int *__restrict__ status,
-                       unsigned int *__restrict__ job_counter) {
+                       int *__restrict__ src_index, int *__restrict__ counts,
+                       int *__restrict__ status, unsigned int *__restrict__ job_counter) {
   prologue_body<T, kPrologueThreads>(blockIdx.x, det, R, C, geom, boxes, class_ids, scores, src_index,
-                                     aux, mw, counts, status, job_counter);
+                                     counts, status, job_counter);
 }
 
 // =====================================================================================
@@ -239,13 +230,13 @@ __global__ void __launch_bounds__(kGatherThreads)
 unmold_prepare_kernel(const TD *__restrict__ det, const TM *__restrict__ mask, int R, int C,
                       int tile_elems, const int *__restrict__ geom, int *__restrict__ boxes,
                       int *__restrict__ class_ids, TD *__restrict__ scores,
-                      int *__restrict__ src_index, BoxAux *__restrict__ aux, int mw,
-                      int *__restrict__ counts, int *__restrict__ status,
-                      unsigned int *__restrict__ job_counter, float *__restrict__ tiles) {
+                      int *__restrict__ src_index, int *__restrict__ counts,
+                      int *__restrict__ status, unsigned int *__restrict__ job_counter,
+                      float *__restrict__ tiles) {
   const int b = blockIdx.y;
   if (static_cast<int>(blockIdx.x) == R) {
-    prologue_body<TD, kGatherThreads>(b, det, R, C, geom, boxes, class_ids, scores, src_index, aux, mw,
-                                      counts, status, job_counter);
+    prologue_body<TD, kGatherThreads>(b, det, R, C, geom, boxes, class_ids, scores, src_index, counts,
+                                      status, job_counter);
     return;
   }
   const int t = blockIdx.x;
@@ -617,14 +608,12 @@ static int check_mask_dims(int mh, int mw) {
 }
 
 extern "C" int mrx_unmold_prologue(const void *d_detections, int det_dtype, int B, int R, int C,
-                                   int mw, const int *d_geom, int *d_boxes, int *d_class_ids,
-                                   void *d_scores, int *d_src_index, int *d_box_aux,
-                                   int *d_counts, int *d_status, unsigned int *d_sched,
-                                   void *stream) {
+                                   const int *d_geom, int *d_boxes, int *d_class_ids,
+                                   void *d_scores, int *d_src_index, int *d_counts,
+                                   int *d_status, unsigned int *d_sched, void *stream) {
   MRX_CHECK_ARG(d_detections && d_geom && d_boxes && d_class_ids && d_scores && d_src_index &&
-                    d_box_aux && d_counts && d_status,
+                    d_counts && d_status,
                 "mrx_unmold_prologue: null pointer");
-  MRX_CHECK_ARG(mw >= 1 && mw <= MRX_MAX_MASK_DIM, "mrx_unmold_prologue: mask width %d", mw);
   MRX_CHECK_ARG(B >= 0 && R >= 1 && C >= 1, "mrx_unmold_prologue: bad sizes B=%d R=%d C=%d", B,
                 R, C);
   MRX_CHECK_ARG(det_dtype == MRX_F32 || det_dtype == MRX_F64,
@@ -634,13 +623,11 @@ extern "C" int mrx_unmold_prologue(const void *d_detections, int det_dtype, int 
   if (det_dtype == MRX_F64) {
     unmold_prologue_kernel<double><<<B, kPrologueThreads, 0, st>>>(
         static_cast<const double *>(d_detections), R, C, d_geom, d_boxes, d_class_ids,
-        static_cast<double *>(d_scores), d_src_index, reinterpret_cast<BoxAux *>(d_box_aux), mw,
-        d_counts, d_status, d_sched);
+        static_cast<double *>(d_scores), d_src_index, d_counts, d_status, d_sched);
   } else {
     unmold_prologue_kernel<float><<<B, kPrologueThreads, 0, st>>>(
         static_cast<const float *>(d_detections), R, C, d_geom, d_boxes, d_class_ids,
-        static_cast<float *>(d_scores), d_src_index, reinterpret_cast<BoxAux *>(d_box_aux), mw,
-        d_counts, d_status, d_sched);
+        static_cast<float *>(d_scores), d_src_index, d_counts, d_status, d_sched);
   }
   MRX_LAUNCH_CHECK("unmold_prologue_kernel");
   return MRX_OK;
@@ -649,10 +636,10 @@ extern "C" int mrx_unmold_prologue(const void *d_detections, int det_dtype, int 
 extern "C" int mrx_unmold_prepare(const void *d_detections, int det_dtype, const void *d_mrcnn_mask,
                                   int mask_dtype, int B, int R, int mh, int mw, int C,
                                   const int *d_geom, int *d_boxes, int *d_class_ids, void *d_scores,
-                                  int *d_src_index, int *d_box_aux, int *d_counts, int *d_status,
+                                  int *d_src_index, int *d_counts, int *d_status,
                                   float *d_tiles, unsigned int *d_sched, void *stream) {
   MRX_CHECK_ARG(d_detections && d_mrcnn_mask && d_geom && d_boxes && d_class_ids && d_scores &&
-                    d_src_index && d_box_aux && d_counts && d_status && d_tiles,
+                    d_src_index && d_counts && d_status && d_tiles,
                 "mrx_unmold_prepare: null pointer");
   MRX_CHECK_ARG(B >= 0 && B <= 65535 && R >= 1 && R <= 65534 && C >= 1 && mh >= 1 && mw >= 1 &&
                     mw <= MRX_MAX_MASK_DIM,
@@ -663,12 +650,11 @@ extern "C" int mrx_unmold_prepare(const void *d_detections, int det_dtype, const
   if (B == 0) return MRX_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(R + 1, B);
-  BoxAux *aux = reinterpret_cast<BoxAux *>(d_box_aux);
 #define MRX_PREPARE(TD, TM)                                                                      \
   unmold_prepare_kernel<TD, TM><<<grid, kGatherThreads, 0, st>>>(                                \
       static_cast<const TD *>(d_detections), static_cast<const TM *>(d_mrcnn_mask), R, C, mh * mw, \
-      d_geom, d_boxes, d_class_ids, static_cast<TD *>(d_scores), d_src_index, aux, mw, d_counts,  \
-      d_status, d_sched, d_tiles)
+      d_geom, d_boxes, d_class_ids, static_cast<TD *>(d_scores), d_src_index, d_counts, d_status,   \
+      d_sched, d_tiles)
   if (det_dtype == MRX_F64 && mask_dtype == MRX_F64) MRX_PREPARE(double, double);
   else if (det_dtype == MRX_F64) MRX_PREPARE(double, float);
   else if (mask_dtype == MRX_F64) MRX_PREPARE(float, double);
@@ -705,12 +691,11 @@ extern "C" int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype, int B,
 }
 
 static int mask_expand_impl(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
-                            const int *d_box_aux,
                             const int *d_counts, const int *d_geom, const long long *d_canvas_off,
                             unsigned char *d_canvas, float *d_values, int B, int R, int mh, int mw,
                             int chunk_bytes, int ctas_per_sm, unsigned int *d_sched,
                             void *stream) {
-  MRX_CHECK_ARG(d_tiles && d_boxes && d_box_aux && d_counts && d_geom && d_canvas_off &&
+  MRX_CHECK_ARG(d_tiles && d_boxes && d_counts && d_geom && d_canvas_off &&
                     d_canvas && d_sched,
                 "mrx_mask_expand: null pointer");
   MRX_CHECK_ARG(B >= 0 && B <= MRX_MAX_BATCH && R >= 1, "mrx_mask_expand: bad sizes B=%d R=%d",
@@ -729,7 +714,6 @@ static int mask_expand_impl(const float *d_tiles, const int *d_tile_index, const
   prm.tiles = d_tiles;
   prm.tile_index = d_tile_index;
   prm.boxes = reinterpret_cast<const int4 *>(d_boxes);
-  prm.aux = reinterpret_cast<const BoxAux *>(d_box_aux);
   prm.counts = d_counts;
   prm.geom = d_geom;
   prm.canvas_off = d_canvas_off;
@@ -783,20 +767,20 @@ static int mask_expand_impl(const float *d_tiles, const int *d_tile_index, const
 }
 
 extern "C" int mrx_mask_expand(const float *d_tiles, const int *d_tile_index, const int *d_boxes,
-                               const int *d_box_aux, const int *d_counts, const int *d_geom,
+                               const int *d_counts, const int *d_geom,
                                const long long *d_canvas_off, unsigned char *d_canvas, int B,
                                int R, int mh, int mw, int chunk_bytes, int ctas_per_sm,
                                unsigned int *d_sched, void *stream) {
-  return mask_expand_impl(d_tiles, d_tile_index, d_boxes, d_box_aux, d_counts, d_geom, d_canvas_off,
+  return mask_expand_impl(d_tiles, d_tile_index, d_boxes, d_counts, d_geom, d_canvas_off,
                           d_canvas, nullptr, B, R, mh, mw, chunk_bytes, ctas_per_sm, d_sched, stream);
 }
 
 extern "C" int mrx_mask_expand_values(const float *d_tiles, const int *d_tile_index,
-                                      const int *d_boxes, const int *d_box_aux, const int *d_counts,
+                                      const int *d_boxes, const int *d_counts,
                                       const int *d_geom, const long long *d_canvas_off,
                                       unsigned char *d_canvas, float *d_values, int B, int R,
                                       int mh, int mw, unsigned int *d_sched, void *stream) {
   MRX_CHECK_ARG(d_values != nullptr, "mrx_mask_expand_values: null pointer");
-  return mask_expand_impl(d_tiles, d_tile_index, d_boxes, d_box_aux, d_counts, d_geom, d_canvas_off,
+  return mask_expand_impl(d_tiles, d_tile_index, d_boxes, d_counts, d_geom, d_canvas_off,
                           d_canvas, d_values, B, R, mh, mw, 0, 0, d_sched, stream);
 }

@@ -91,7 +91,6 @@ class UnmoldEngine:
         self.d_class_ids = torch.empty((B, R), dtype=i32, device=dev)
         self.d_scores = torch.empty((B, R), dtype=_torch_dtype(self.det_dtype), device=dev)
         self.d_src_index = torch.empty((B, R), dtype=i32, device=dev)
-        self.d_box_aux = torch.zeros((B, R, 4), dtype=i32, device=dev)
         self.d_counts = torch.zeros((B,), dtype=i32, device=dev)
         self.d_status = torch.zeros((B,), dtype=i32, device=dev)
         self.d_tiles = torch.empty((B, R, self.mh, self.mw), dtype=torch.float32, device=dev)
@@ -183,7 +182,7 @@ class UnmoldEngine:
             _ptr(d_detections), _dtype_code(self.det_dtype), _ptr(d_mrcnn_mask),
             _dtype_code(self.mask_dtype), n, self.R, self.mh, self.mw, self.C,
             _ptr(self.d_geom), _ptr(self.d_boxes), _ptr(self.d_class_ids), _ptr(self.d_scores),
-            _ptr(self.d_src_index), _ptr(self.d_box_aux), _ptr(self.d_counts),
+            _ptr(self.d_src_index), _ptr(self.d_counts),
             _ptr(self.d_status), _ptr(self.d_tiles), _ptr(self.d_sched), st),
             "mrx_unmold_prepare")
         if expand:
@@ -201,7 +200,6 @@ class UnmoldEngine:
         base = _ptr(self.d_canvas) if canvas_ptr is None else C.c_void_p(int(canvas_ptr))
         N.check(self.lib.mrx_mask_expand(
             _ptr(self.d_tiles[b0:]), _ptr(self.d_src_index[b0:]), _ptr(self.d_boxes[b0:]),
-            _ptr(self.d_box_aux[b0:]),
             _ptr(self.d_counts[b0:]), _ptr(self.d_geom[b0:]),
             _ptr(self.d_canvas_off[b0:]), base, b1 - b0, self.R, self.mh, self.mw,
             self.chunk_bytes, self.ctas_per_sm, _ptr(self.d_sched),
@@ -214,8 +212,7 @@ class UnmoldEngine:
         if d_values.dtype != _torch().float32 or d_values.numel() < int(self._offsets[n]):
             raise ValueError("d_values must be float32 with one element per canvas byte")
         N.check(self.lib.mrx_mask_expand_values(
-            _ptr(self.d_tiles), _ptr(self.d_src_index), _ptr(self.d_boxes), _ptr(self.d_box_aux),
-            _ptr(self.d_counts),
+            _ptr(self.d_tiles), _ptr(self.d_src_index), _ptr(self.d_boxes), _ptr(self.d_counts),
             _ptr(self.d_geom), _ptr(self.d_canvas_off), _ptr(self.d_canvas), _ptr(d_values),
             n, self.R, self.mh, self.mw, _ptr(self.d_sched), N.stream_ptr(stream)),
             "mrx_mask_expand_values")

@@ -40,15 +40,15 @@ def test_host_side_argument_validation():
     assert lib.mrx_anchor_count(1024, 1024, strides, 9, 3, 1, C.byref(out)) == -2     # > MRX_MAX_LEVELS
     assert b"n_levels" in lib.mrx_last_error()
     assert lib.mrx_anchors(None, 1024, 1024, None, None, strides, 5, 3, 1, None) == -1
-    assert lib.mrx_mask_expand(None, None, None, None, None, None, None, None, 1, 100, 28, 28, 0,
+    assert lib.mrx_mask_expand(None, None, None, None, None, None, None, 1, 100, 28, 28, 0,
                                0, None, None) == -1
-    assert lib.mrx_mask_expand_values(None, None, None, None, None, None, None, None, None, 1, 100,
+    assert lib.mrx_mask_expand_values(None, None, None, None, None, None, None, None, 1, 100,
                                       28, 28, None, None) == -1
     p16 = C.c_void_p(16)
     assert lib.mrx_mask_expand_packed(p16, None, p16, p16, p16, p16, p16, 1, 100, 28, 32, 1024,
                                       p16, None) == -2      # mask tiles wider than 30 columns
     assert b"30" in lib.mrx_last_error()
-    assert lib.mrx_unmold_prepare(p16, 0, p16, 3, 1, 100, 28, 28, 81, p16, p16, p16, p16, p16, p16,
+    assert lib.mrx_unmold_prepare(p16, 0, p16, 3, 1, 100, 28, 28, 81, p16, p16, p16, p16, p16,
                                   p16, p16, p16, p16, None) == -1      # bad mask dtype
     assert lib.mrx_peer_export(None, None) == -1 and lib.mrx_peer_wait(None, 1, 1, None) == -1
 
