@@ -326,6 +326,12 @@ def timed_device(ctx, fn, reps):
     return ms[len(ms) // 2], ms[0]
 
 
+def _bytesum(torch, t, chunk=1 << 28):
+    """Sum of a uint8 tensor's bytes (checksum of a gathered buffer), 256 MB at a time: the
+    widening reduction materialises an int64 copy of its input."""
+    return sum(int(c.sum(dtype=torch.int64).item()) for c in t.split(chunk)) if t.numel() else 0
+
+
 def gather_section(ctx, eng, d_det, d_msk, n_images, masks_total, layout_note, chunks=4, reps=3):
     """One step + the gather of every rank's output to rank 0, both layouts, both transports.
     Returns the `gather` dict.  Rank 0's NVLink ingress bounds all of them: (world-1)/world of
@@ -347,8 +353,8 @@ def gather_section(ctx, eng, d_det, d_msk, n_images, masks_total, layout_note, c
     # reference content of this rank (local run) -> checksums rank 0 verifies the gathers with
     eng.enqueue(d_det, d_msk)
     d_packed, _ = eng.enqueue_expand_packed()
-    sum_bytes = int(eng.d_canvas[:byte_total].sum(dtype=torch.int64).item())
-    sum_packed = int(d_packed[:pk_total].to(torch.int64).sum().item())
+    sum_bytes = _bytesum(torch, eng.d_canvas[:byte_total])
+    sum_packed = _bytesum(torch, d_packed[:pk_total])
     sums = [ctx.gather_floats(sum_bytes), ctx.gather_floats(sum_packed)]
 
     def verify(slot_fn, which, total):
@@ -356,7 +362,7 @@ def gather_section(ctx, eng, d_det, d_msk, n_images, masks_total, layout_note, c
             return True
         ok = True
         for r in range(world):
-            got = int(slot_fn(r)[:total].to(torch.int64).sum().item())
+            got = _bytesum(torch, slot_fn(r)[:total])
             ok = ok and (got == int(sums[which][r]))
         return ok
 

@@ -44,7 +44,7 @@ def child(args):
     torch.cuda.synchronize()
     counts = eng.d_counts[:args.batch].cpu().numpy()
     nbytes = eng.canvas_bytes(counts) + int(counts.sum()) * 3160
-    digest = int(eng.d_canvas[:int(eng._offsets[args.batch])].to(torch.int64).sum().item())
+    digest = bench._bytesum(torch, eng.d_canvas[:int(eng._offsets[args.batch])])
 
     def timeit(fn):
         ts = []
