@@ -390,6 +390,17 @@ def gather_section(ctx, eng, d_det, d_msk, n_images, masks_total, layout_note, c
         run_nccl()                                   # warm-up (NCCL channels, buffers)
         med, best = timed_device(ctx, run_nccl, reps)
         ok = verify(g.slot, which, total)
+
+        def run_transport_only():                    # the same bytes, no kernels: the wire alone
+            g.begin(1, [[(0, total)]] * world)
+            g.post(local, 0, total)
+            g.wait()
+
+        t_med, _ = timed_device(ctx, run_transport_only, reps)
+        res[f"{layout}_transport_only"] = {
+            "ms": t_med, "ingress_gbs": into_rank0 / (t_med * 1e-3) / 1e9,
+            "what": "NCCL send/recv of the finished buffers into rank 0, no compute: the wire time "
+                    "the gather variants are compared with"}
         res[f"{layout}_nccl"] = {
             "value": masks_total / (med * 1e-3), "ms": med, "ms_best": best,
             "bytes_into_rank0": into_rank0, "ingress_gbs": into_rank0 / (med * 1e-3) / 1e9,
