@@ -61,10 +61,11 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.y;
   const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
-  const long long npix = static_cast<long long>(H) * W;
-  const long long p0 = static_cast<long long>(blockIdx.x) * kCompThreads;
+  // (the host checks H*W < 2^31: pixel indices are 32-bit, their byte offsets 64-bit)
+  const unsigned npix = static_cast<unsigned>(H) * static_cast<unsigned>(W);
+  const unsigned p0 = blockIdx.x * static_cast<unsigned>(kCompThreads);
   if (p0 >= npix) return;
-  const int npx = static_cast<int>(min(static_cast<long long>(kCompThreads), npix - p0));
+  const int npx = static_cast<int>(min(static_cast<unsigned>(kCompThreads), npix - p0));
   const int N = counts[b];
   const int t = threadIdx.x;
 
@@ -88,8 +89,9 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   }
   if (kCull) {
     // rows / columns the CTA's pixels span (a run of consecutive pixels in row-major order)
-    const int ya = static_cast<int>(p0 / W), yb = static_cast<int>((p0 + npx - 1) / W);
-    const int xa = ya == yb ? static_cast<int>(p0 - static_cast<long long>(ya) * W) : 0;
+    const int ya = static_cast<int>(p0 / static_cast<unsigned>(W));
+    const int yb = static_cast<int>((p0 + npx - 1) / static_cast<unsigned>(W));
+    const int xa = ya == yb ? static_cast<int>(p0 - static_cast<unsigned>(ya) * W) : 0;
     const int xb = ya == yb ? xa + npx : W;   // exclusive
     int running = 0;
     for (int base = 0; base < N; base += kCompThreads) {
@@ -118,7 +120,7 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   if (N > 0) {
     // 256*N is a multiple of 16 and so is every canvas slot offset: whole uint4 loads; the
     // slot holds round_up(H*W*N, 16) bytes, so the last block may read its pad bytes
-    const unsigned char *src = canvas + canvas_off[b] + p0 * N;
+    const unsigned char *src = canvas + canvas_off[b] + static_cast<size_t>(p0) * N;
     const int n16 = (npx * N + 15) >> 4;
     const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
     uint4 *d4 = reinterpret_cast<uint4 *>(s_can);
@@ -137,7 +139,7 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   __syncthreads();
   if (t >= npx) return;
 
-  const unsigned char *ip = images + image_off[b] + (p0 + t) * 3;
+  const unsigned char *ip = images + image_off[b] + static_cast<size_t>(p0 + t) * 3;
   unsigned v0 = ip[0], v1 = ip[1], v2 = ip[2];
   const unsigned char *lut_b = kLut ? lut + static_cast<size_t>(b) * R * 768 : nullptr;
   auto apply = [&](int i) {
@@ -188,7 +190,7 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
     for (int i = 0; i < N; ++i)
       if (mp[i]) apply(i);
   }
-  unsigned char *op = out + image_off[b] + (p0 + t) * 3;
+  unsigned char *op = out + image_off[b] + static_cast<size_t>(p0 + t) * 3;
   op[0] = static_cast<unsigned char>(v0);   // astype(uint8): modulo 256
   op[1] = static_cast<unsigned char>(v1);
   op[2] = static_cast<unsigned char>(v2);
@@ -220,7 +222,7 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
                       "mrx_composite_masks: R=%d needs %zu B of shared memory (limit %d)", R, smem,
                       max_optin);
   const long long blocks = (max_pixels + kCompThreads - 1) / kCompThreads;
-  MRX_CHECK_SUPPORTED(blocks <= 0x7fffffffLL, "mrx_composite_masks: image too large");
+  MRX_CHECK_SUPPORTED(max_pixels < 0x7fffffffLL - kCompThreads, "mrx_composite_masks: image too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(B));
   const int4 *boxes4 = reinterpret_cast<const int4 *>(d_boxes);

@@ -58,6 +58,64 @@ def _is_triple(x):
     return len(x) == 3 and not hasattr(x[0], "__len__")
 
 
+class CompositeStage:
+    """Device-side inputs of the overlay for one planned batch (images, blend table, scratch),
+    staged once; `run()` launches `mrx_composite_masks` on the engine's current canvas.  Lets a
+    pipeline (or a benchmark) separate the upload of the images from the kernel."""
+
+    def __init__(self, engine, images, colors, alpha=0.5, table=None):
+        import torch
+
+        N.require_cuda()
+        self.lib = N.load()
+        self.engine = engine
+        B = engine._n_images
+        if B == 0 or len(images) != B:
+            raise ValueError(f"{len(images)} images for a plan of {B}")
+        dev = engine.device
+        geom = engine._geom_host
+        self.geom = geom
+        sizes = [int(geom[b][0]) * int(geom[b][1]) * 3 for b in range(B)]
+        offs = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(sizes, out=offs[1:])
+        self.offs = offs
+        self.d_in = torch.empty(int(offs[-1]), dtype=torch.uint8, device=dev)
+        for b, img in enumerate(images):
+            t = img if torch.is_tensor(img) else torch.from_numpy(np.ascontiguousarray(img))
+            if t.dtype != torch.uint8 or t.numel() != sizes[b]:
+                raise ValueError(f"image {b}: expected uint8 {geom[b][0]}x{geom[b][1]}x3")
+            self.d_in[int(offs[b]):int(offs[b + 1])].copy_(t.reshape(-1), non_blocking=True)
+        self.d_out = torch.empty_like(self.d_in)
+        shared = len(colors) > 0 and _is_triple(colors[0])
+        if not shared and len(colors) != B:
+            raise ValueError("colors: one list of RGB triples, or one list per image")
+        tab = np.stack([blend_table(colors if shared else colors[b], alpha, engine.R)
+                        for b in range(B)])
+        self.alpha = alpha
+        self.d_tab = torch.from_numpy(tab).to(dev)
+        self.d_off = torch.from_numpy(offs[:B].copy()).to(dev)
+        self.max_px = max(int(geom[b][0]) * int(geom[b][1]) for b in range(B))
+        use_table = _table_is_valid(tab, alpha) if table is None else bool(table)
+        if use_table and not _table_is_valid(tab, alpha):
+            raise ValueError("the tabulated blend needs alpha and colours in [0, 1]")
+        self.d_lut = torch.empty((B * engine.R * 768,), dtype=torch.uint8, device=dev) \
+            if use_table else None
+
+    def run(self, stream=None, cull=True):
+        eng = self.engine
+        N.check(self.lib.mrx_composite_masks(
+            _ptr(eng.d_canvas), _ptr(eng.d_canvas_off), _ptr(eng.d_counts),
+            _ptr(eng.d_geom), _ptr(eng.d_boxes), _ptr(self.d_in), _ptr(self.d_off),
+            _ptr(self.d_tab), C.c_double(1 - self.alpha),
+            _ptr(self.d_lut) if self.d_lut is not None else C.c_void_p(0),
+            1 if cull else 0,        # the engine's canvas: instance i is zero outside its box
+            _ptr(self.d_out), eng._n_images, eng.R, C.c_longlong(self.max_px),
+            N.stream_ptr(stream)), "mrx_composite_masks")
+        offs, geom = self.offs, self.geom
+        return [self.d_out[int(offs[b]):int(offs[b + 1])].view(int(geom[b][0]), int(geom[b][1]), 3)
+                for b in range(eng._n_images)]
+
+
 def composite_batch(engine, images, colors, alpha=0.5, stream=None, table=None, cull=True):
     """Overlay the masks an `UnmoldEngine` holds on its device canvas (after `enqueue`).
 
@@ -69,44 +127,7 @@ def composite_batch(engine, images, colors, alpha=0.5, stream=None, table=None, 
     cull: visit, per block of pixels, only the instances whose box meets it (valid because the
     expand kernel never sets a pixel outside the box; False walks every instance -- same output).
     """
-    import torch
-
-    N.require_cuda()
-    lib = N.load()
-    B = engine._n_images
-    if B == 0 or len(images) != B:
-        raise ValueError(f"{len(images)} images for a plan of {B}")
-    dev = engine.device
-    geom = engine._geom_host
-    sizes = [int(geom[b][0]) * int(geom[b][1]) * 3 for b in range(B)]
-    offs = np.zeros(B + 1, dtype=np.int64)
-    np.cumsum(sizes, out=offs[1:])
-    d_in = torch.empty(int(offs[-1]), dtype=torch.uint8, device=dev)
-    for b, img in enumerate(images):
-        t = img if torch.is_tensor(img) else torch.from_numpy(np.ascontiguousarray(img))
-        if t.dtype != torch.uint8 or t.numel() != sizes[b]:
-            raise ValueError(f"image {b}: expected uint8 {geom[b][0]}x{geom[b][1]}x3")
-        d_in[int(offs[b]):int(offs[b + 1])].copy_(t.reshape(-1), non_blocking=True)
-    d_out = torch.empty_like(d_in)
-    shared = len(colors) > 0 and _is_triple(colors[0])
-    if not shared and len(colors) != B:
-        raise ValueError("colors: one list of RGB triples, or one list per image")
-    tab = np.stack([blend_table(colors if shared else colors[b], alpha, engine.R)
-                    for b in range(B)])
-    d_tab = torch.from_numpy(tab).to(dev)
-    d_off = torch.from_numpy(offs[:B].copy()).to(dev)
-    max_px = max(int(geom[b][0]) * int(geom[b][1]) for b in range(B))
-    d_lut = torch.empty((B * engine.R * 768,), dtype=torch.uint8, device=dev) \
-        if (table is None and _table_is_valid(tab, alpha)) or table else None
-    N.check(lib.mrx_composite_masks(
-        _ptr(engine.d_canvas), _ptr(engine.d_canvas_off), _ptr(engine.d_counts),
-        _ptr(engine.d_geom), _ptr(engine.d_boxes), _ptr(d_in), _ptr(d_off), _ptr(d_tab),
-        C.c_double(1 - alpha), _ptr(d_lut) if d_lut is not None else C.c_void_p(0),
-        1 if cull else 0,        # the engine's canvas: instance i is zero outside its box
-        _ptr(d_out), B, engine.R, C.c_longlong(max_px), N.stream_ptr(stream)),
-        "mrx_composite_masks")
-    return [d_out[int(offs[b]):int(offs[b + 1])].view(int(geom[b][0]), int(geom[b][1]), 3)
-            for b in range(B)]
+    return CompositeStage(engine, images, colors, alpha, table=table).run(stream, cull)
 
 
 def apply_masks(image, boxes, masks, colors, alpha=0.5):

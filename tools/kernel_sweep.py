@@ -64,6 +64,18 @@ def child(args):
     pre_med, _ = timeit(lambda: eng.enqueue(d_det, d_msk, expand=False))
     pk_med, pk_min = timeit(lambda: eng.enqueue_expand_packed())
     pack_med, _ = timeit(lambda: eng.pack_masks())
+    # mask overlay on the device canvas: kernel alone (inputs staged once), all four forms
+    import random
+    from matterport_maskrcnn_with_tensorflow_serving_b200 import synth, visualize
+    rng = np.random.default_rng(0)
+    img = torch.from_numpy(synth.synth_rgb_image(rng, 1024, 1024)).cuda()
+    colors = visualize.random_colors(100, rng=random.Random(0))
+    comp = {}
+    for table in (None, False):
+        for cull in (True, False):
+            st = visualize.CompositeStage(eng, [img] * args.batch, colors, 0.5, table=table)
+            med, _ = timeit(lambda: st.run(cull=cull))
+            comp[("table" if table is None else "exact") + ("+cull" if cull else "")] = round(med, 4)
     print(json.dumps({"variant": os.environ.get("MRX_EXPAND_TEAMS", "default"),
                       "flags": os.environ.get("MRX_EXPAND_FLAGS", ""),
                       "bits_warps": os.environ.get("MRX_BITS_WARPS", "default"),
@@ -72,7 +84,8 @@ def child(args):
                       "expand_GBps": round(nbytes / exp_med / 1e6, 1), "step_ms": round(step_med, 4),
                       "prologue_gather_ms": round(pre_med, 4),
                       "expand_packed_ms": round(pk_med, 4), "expand_packed_ms_min": round(pk_min, 4),
-                      "pack_kernel_ms": round(pack_med, 4), "ones": digest}), flush=True)
+                      "pack_kernel_ms": round(pack_med, 4), "composite_ms": comp,
+                      "ones": digest}), flush=True)
 
 
 def main():
