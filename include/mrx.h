@@ -199,21 +199,13 @@ int mrx_mold_image_batch(const unsigned char *d_src, int B, int src_h, int src_w
  *   d_images / d_out: uint8 H_b x W_b x 3 images of the batch, image b at byte offset
  *   d_image_off[b] (int64) in both;  d_blend [B,R,3] float64 = alpha * color[c] * 255,
  *   evaluated by the caller in float64 in that order;  d_boxes [B,R,4] as written by
- *   mrx_unmold_prologue;  max_pixels = max_b H_b * W_b (grid sizing).
- *   d_lut: NULL, or B*R*768 bytes of device scratch.  With scratch the library first tabulates
- *   the blend -- the same float64 expression, once per (image, instance, channel, value 0..255)
- *   -- and the per-pixel walk looks it up; identical output, but ONLY valid when every blend
- *   keeps values in 0..255, i.e. one_minus_alpha >= 0, every d_blend entry >= 0 and
- *   255 * one_minus_alpha + max(d_blend) < 256 (alpha and colours in [0,1]); the caller checks.
- *   masks_in_boxes: non-zero promises that instance i is zero outside d_boxes[b][i] (true for a
- *   canvas written by mrx_mask_expand): each block of pixels then visits only the instances
- *   whose box meets it.  0: every instance byte of every pixel is examined (arbitrary masks). */
+ *   mrx_unmold_prologue;  max_pixels = max_b H_b * W_b (grid sizing). */
 int mrx_composite_masks(const unsigned char *d_canvas, const long long *d_canvas_off,
                         const int *d_counts, const int *d_geom, const int *d_boxes,
                         const unsigned char *d_images, const long long *d_image_off,
                         const double *d_blend, double one_minus_alpha,
-                        unsigned char *d_lut, int masks_in_boxes, unsigned char *d_out,
-                        int B, int R, long long max_pixels, void *stream);
+                        unsigned char *d_out, int B, int R, long long max_pixels,
+                        void *stream);
 
 /* ---------------------------------------------------------------- packed masks (8f) */
 /* EXTENSION (not the reference layout): bit-packed copy of the canvases for transport.

@@ -8,56 +8,30 @@
 // Doing that on the device canvas mrx_mask_expand just wrote removes the 105 MB per image
 // device -> host copy of the masks for callers that only want the overlay.
 //
+// Alternatives measured this round and removed again (profiles/README.md): tabulating the blend
+// per (instance, channel, value) instead of evaluating it in fp64 per pixel (0.884 vs 0.885 ms)
+// and restricting every block of pixels to the instances whose box meets it (0.947 ms: slower);
+// the kernel is bound by the stage-then-walk structure (global-load latency), not by the blend.
+//
 // HBM-read bound: N bytes of canvas per pixel (3.36 GB per config-2 batch) + 3 B in + 3 B out.
 // One CTA = 256 consecutive pixels of one image: their 256*N canvas bytes are contiguous
 // (N innermost) and are staged into shared memory with 16-byte loads; thread t then walks
 // pixel t's N bytes (4 at a time when N % 4 == 0: most words are zero) and applies the
 // blends of the set instances in instance order -- fp64 with explicit _rn intrinsics in
 // NumPy's operation order, truncation to uint32 after every instance: bit-exact.
-//
-// Two forms of the blend, same result:
-//   exact   v = uint32(float64(v) * (1 - alpha) + blend[i][c]) evaluated per set (pixel, instance):
-//           twelve fp64-pipe instructions per blend, any alpha / colours (values may leave 0..255);
-//   table   when every blend keeps values inside 0..255 (alpha and colours in [0, 1]: what
-//           display_instances passes) the step is a function of (instance, channel, v) only:
-//           composite_lut_kernel evaluates the SAME fp64 expression once per (b, i, c, v) --
-//           768 bytes per instance, identity rows for skipped instances -- and the pixel walk
-//           does three byte loads per blend from that table (L1-resident) instead.
 #include "common.cuh"
 
 namespace mrx {
 
 constexpr int kCompThreads = 256;
 
-// lut[b][i][c][v] = uint8 of the blend of instance i, channel c, applied to value v
-__global__ void __launch_bounds__(256)
-composite_lut_kernel(const int *__restrict__ counts, const int4 *__restrict__ boxes,
-                     const double *__restrict__ blend, double one_minus_alpha,
-                     unsigned char *__restrict__ lut, int R) {
-  const int i = blockIdx.x, b = blockIdx.y;
-  if (i >= counts[b]) return;
-  const int4 bx = boxes[static_cast<size_t>(b) * R + i];
-  const bool skip = (bx.x | bx.y | bx.z | bx.w) == 0;   // upstream: `if not np.any(boxes[i]): continue`
-  const unsigned v = threadIdx.x;
-  for (int c = 0; c < 3; ++c) {
-    const double bl = blend[(static_cast<size_t>(b) * R + i) * 3 + c];
-    const unsigned r = __double2uint_rz(__dadd_rn(__dmul_rn(static_cast<double>(v), one_minus_alpha), bl));
-    lut[((static_cast<size_t>(b) * R + i) * 3 + c) * 256 + v] = static_cast<unsigned char>(skip ? v : r);
-  }
-}
-
-// kCull: the canvas was written by mrx_mask_expand, so instance i is zero outside its box: the
-// CTA first lists (in order) the instances whose box meets its pixels -- about ten of a hundred
-// -- and every pixel then looks at those bytes only, instead of walking all N.
-template <bool kLut, bool kCull>
 __global__ void __launch_bounds__(kCompThreads)
 composite_masks_kernel(const unsigned char *__restrict__ canvas,
                        const long long *__restrict__ canvas_off,
                        const int *__restrict__ counts, const int *__restrict__ geom,
                        const int4 *__restrict__ boxes, const unsigned char *__restrict__ images,
                        const long long *__restrict__ image_off, const double *__restrict__ blend,
-                       double one_minus_alpha, const unsigned char *__restrict__ lut,
-                       unsigned char *__restrict__ out, int R) {
+                       double one_minus_alpha, unsigned char *__restrict__ out, int R) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.y;
   const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
@@ -74,48 +48,11 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   unsigned char *s_skip = smem + ((static_cast<size_t>(R) * 3 * sizeof(double) + 15) & ~static_cast<size_t>(15));
   unsigned char *s_can = s_skip + ((R + 15) & ~15);
 
-  __shared__ int s_wcnt[kCompThreads / 32];
-  __shared__ int s_nlist;
-  // the candidate list reuses the skip-flag bytes as 16-bit entries when R is small enough
-  // for them to fit (R + 15 bytes hold R/2 entries): it has its own array instead
-  unsigned short *s_list = reinterpret_cast<unsigned short *>(s_can + ((static_cast<size_t>(kCompThreads) * R + 31) & ~static_cast<size_t>(15)));
-  if (!kLut) {
-    for (int i = t; i < N * 3; i += kCompThreads)
-      s_blend[i] = blend[static_cast<size_t>(b) * R * 3 + i];
-    for (int i = t; i < N; i += kCompThreads) {
-      const int4 bx = boxes[static_cast<size_t>(b) * R + i];
-      s_skip[i] = (bx.x | bx.y | bx.z | bx.w) == 0;   // upstream: `if not np.any(boxes[i]): continue`
-    }
-  }
-  if (kCull) {
-    // rows / columns the CTA's pixels span (a run of consecutive pixels in row-major order)
-    const int ya = static_cast<int>(p0 / static_cast<unsigned>(W));
-    const int yb = static_cast<int>((p0 + npx - 1) / static_cast<unsigned>(W));
-    const int xa = ya == yb ? static_cast<int>(p0 - static_cast<unsigned>(ya) * W) : 0;
-    const int xb = ya == yb ? xa + npx : W;   // exclusive
-    int running = 0;
-    for (int base = 0; base < N; base += kCompThreads) {
-      const int i = base + t;
-      bool hit = false;
-      if (i < N) {
-        const int4 bx = boxes[static_cast<size_t>(b) * R + i];   // (y1, x1, y2, x2)
-        hit = bx.x <= yb && bx.z > ya && bx.y < xb && bx.w > xa;
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, hit);
-      if ((t & 31) == 0) s_wcnt[t >> 5] = __popc(bal);
-      __syncthreads();
-      int before = running, total = 0;
-#pragma unroll
-      for (int w = 0; w < kCompThreads / 32; ++w) {
-        const int c = s_wcnt[w];
-        if (w < (t >> 5)) before += c;
-        total += c;
-      }
-      if (hit) s_list[before + __popc(bal & ((1u << (t & 31)) - 1u))] = static_cast<unsigned short>(i);
-      running += total;
-      __syncthreads();
-    }
-    if (t == 0) s_nlist = running;
+  for (int i = t; i < N * 3; i += kCompThreads)
+    s_blend[i] = blend[static_cast<size_t>(b) * R * 3 + i];
+  for (int i = t; i < N; i += kCompThreads) {
+    const int4 bx = boxes[static_cast<size_t>(b) * R + i];
+    s_skip[i] = (bx.x | bx.y | bx.z | bx.w) == 0;   // upstream: `if not np.any(boxes[i]): continue`
   }
   if (N > 0) {
     // 256*N is a multiple of 16 and so is every canvas slot offset: whole uint4 loads; the
@@ -141,15 +78,7 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
 
   const unsigned char *ip = images + image_off[b] + static_cast<size_t>(p0 + t) * 3;
   unsigned v0 = ip[0], v1 = ip[1], v2 = ip[2];
-  const unsigned char *lut_b = kLut ? lut + static_cast<size_t>(b) * R * 768 : nullptr;
   auto apply = [&](int i) {
-    if (kLut) {   // same fp64 expression, evaluated once per (instance, channel, value)
-      const unsigned char *l = lut_b + i * 768;
-      v0 = __ldg(l + v0);
-      v1 = __ldg(l + 256 + v1);
-      v2 = __ldg(l + 512 + v2);
-      return;
-    }
     if (s_skip[i]) return;
     const double *bl = s_blend + i * 3;
     v0 = __double2uint_rz(__dadd_rn(__dmul_rn(static_cast<double>(v0), one_minus_alpha), bl[0]));
@@ -157,13 +86,7 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
     v2 = __double2uint_rz(__dadd_rn(__dmul_rn(static_cast<double>(v2), one_minus_alpha), bl[2]));
   };
   const unsigned char *mp = s_can + static_cast<size_t>(t) * N;
-  if (kCull) {
-    const int nl = s_nlist;
-    for (int c = 0; c < nl; ++c) {   // instance order is preserved by the compaction
-      const int i = s_list[c];
-      if (mp[i]) apply(i);
-    }
-  } else if ((N & 3) == 0) {
+  if ((N & 3) == 0) {
     // ~3 % of the bytes are set: test five words (20 instances) with one OR before looking
     // at any of them
     const uint32_t *mw = reinterpret_cast<const uint32_t *>(mp);
@@ -202,7 +125,6 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
                                    const int *d_counts, const int *d_geom, const int *d_boxes,
                                    const unsigned char *d_images, const long long *d_image_off,
                                    const double *d_blend, double one_minus_alpha,
-                                   unsigned char *d_lut, int masks_in_boxes,
                                    unsigned char *d_out, int B, int R, long long max_pixels,
                                    void *stream) {
   using namespace mrx;
@@ -216,35 +138,20 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
   if (int rc = current_device_info(&dev)) return rc;
   const int max_optin = dev.max_smem_optin;
   const size_t smem = ((static_cast<size_t>(R) * 3 * sizeof(double) + 15) & ~static_cast<size_t>(15)) +
-                      ((R + 15) & ~15) + static_cast<size_t>(kCompThreads) * R + 32 +
-                      static_cast<size_t>(R) * sizeof(unsigned short) + 16;
+                      ((R + 15) & ~15) + static_cast<size_t>(kCompThreads) * R + 16;
   MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(max_optin),
                       "mrx_composite_masks: R=%d needs %zu B of shared memory (limit %d)", R, smem,
                       max_optin);
   const long long blocks = (max_pixels + kCompThreads - 1) / kCompThreads;
   MRX_CHECK_SUPPORTED(max_pixels < 0x7fffffffLL - kCompThreads, "mrx_composite_masks: image too large");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static SmemCache cache;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(composite_masks_kernel), &cache,
+                                   dev.device, static_cast<int>(smem)))
+    return rc;
   dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(B));
-  const int4 *boxes4 = reinterpret_cast<const int4 *>(d_boxes);
-  if (d_lut != nullptr) {
-    composite_lut_kernel<<<dim3(R, B), 256, 0, st>>>(d_counts, boxes4, d_blend, one_minus_alpha, d_lut, R);
-    MRX_LAUNCH_CHECK("composite_lut_kernel");
-  }
-#define MRX_COMPOSITE(LUT, CULL)                                                                   \
-  do {                                                                                             \
-    static SmemCache cache;                                                                        \
-    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(composite_masks_kernel<LUT, CULL>), \
-                                     &cache, dev.device, static_cast<int>(smem)))                  \
-      return rc;                                                                                   \
-    composite_masks_kernel<LUT, CULL><<<grid, kCompThreads, smem, st>>>(                           \
-        d_canvas, d_canvas_off, d_counts, d_geom, boxes4, d_images, d_image_off, d_blend,          \
-        one_minus_alpha, d_lut, d_out, R);                                                         \
-  } while (0)
-  if (d_lut != nullptr && masks_in_boxes) MRX_COMPOSITE(true, true);
-  else if (d_lut != nullptr) MRX_COMPOSITE(true, false);
-  else if (masks_in_boxes) MRX_COMPOSITE(false, true);
-  else MRX_COMPOSITE(false, false);
-#undef MRX_COMPOSITE
+  composite_masks_kernel<<<grid, kCompThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      d_canvas, d_canvas_off, d_counts, d_geom, reinterpret_cast<const int4 *>(d_boxes), d_images,
+      d_image_off, d_blend, one_minus_alpha, d_out, R);
   MRX_LAUNCH_CHECK("composite_masks_kernel");
   return MRX_OK;
 }

@@ -49,10 +49,6 @@
 
 #include "expand.cuh"
 
-#ifndef MRX_DEFAULT_WALK
-#define MRX_DEFAULT_WALK 1
-#endif
-
 namespace mrx {
 
 namespace team {
@@ -156,16 +152,9 @@ __device__ __forceinline__ void team_bar(int id, int nthreads) {
 }
 
 // kValues: also store every pre-threshold sample as float (test instantiation, see the header).
-// kWalk: 0 = every lane advances the vertical source coordinate itself, row by row;
-//        1 = lane i computes row i's weight once per item, the rows read it with a shuffle.
-// kBufs: tile buffers per team.  1: a team zeroes, fills and drains one buffer in turn (other
-//        teams cover the drain).  2: the team fills one buffer while the previous tile drains
-//        from the other -- the store of tile t is only waited for before tile t + 2 reuses
-//        its buffer.
-template <int kTeams, int kTeamWarps, int kTileRows, bool kValues, int kWalk, int kBufs>
+template <int kTeams, int kTeamWarps, int kTileRows, bool kValues>
 __global__ void __launch_bounds__(kTeams * kTeamWarps * 32, 1)
 mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
-  static_assert(kBufs == 1 || kBufs == 2, "one or two tile buffers per team");
   static_assert(kTileRows <= 32 && kTeamWarps >= 3, "one store lane per tile row; cull + decode warps");
   static_assert(2 * kTeams + 1 <= 16, "two named barriers per team");
   extern __shared__ __align__(128) unsigned char smem[];
@@ -180,13 +169,11 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
   const int rowcap = (buf_bytes / kTileRows) & ~15;
 
   // ---- carve shared memory: [team buffers][team entry lists][team job descriptors][prefix]
-  constexpr int kAllBufs = kTeams * kBufs;
-  unsigned char *const s_buf0 = smem + static_cast<size_t>(tm) * kBufs * buf_bytes;
-  unsigned char *s_buf = s_buf0;   // the buffer of the tile being drawn (alternates when kBufs == 2)
-  TEntry *s_ent = reinterpret_cast<TEntry *>(smem + static_cast<size_t>(kAllBufs) * buf_bytes) + tm * kCand;
-  TJob *s_job = reinterpret_cast<TJob *>(smem + static_cast<size_t>(kAllBufs) * buf_bytes +
+  unsigned char *s_buf = smem + static_cast<size_t>(tm) * buf_bytes;
+  TEntry *s_ent = reinterpret_cast<TEntry *>(smem + static_cast<size_t>(kTeams) * buf_bytes) + tm * kCand;
+  TJob *s_job = reinterpret_cast<TJob *>(smem + static_cast<size_t>(kTeams) * buf_bytes +
                                          static_cast<size_t>(kTeams) * kCand * sizeof(TEntry)) + tm * 2;
-  int *s_prefix = reinterpret_cast<int *>(smem + static_cast<size_t>(kAllBufs) * buf_bytes +
+  int *s_prefix = reinterpret_cast<int *>(smem + static_cast<size_t>(kTeams) * buf_bytes +
                                           static_cast<size_t>(kTeams) * kCand * sizeof(TEntry) +
                                           static_cast<size_t>(kTeams) * 2 * sizeof(TJob));
   __shared__ int s_total;
@@ -218,7 +205,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
   __syncthreads();
   const int total = s_total;
   const int bar_id = 1 + tm;
-  uint32_t buf_addr = smem_u32(s_buf);
+  const uint32_t buf_addr = smem_u32(s_buf);
 
   // decode tile `j` into *out (one thread); cur_b is the caller's search cursor
   // (per-image constants live in shared memory: registers would cost every thread)
@@ -381,7 +368,7 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
       const int rem = ((kk * pitch) >> 4) - tt;   // 16-byte words from this thread's first one on
       // the largest tile buffer a team can get (232 448 B of shared memory per CTA)
       constexpr int kMaxBuf = (232448 - kTeams * (kCand * static_cast<int>(sizeof(TEntry)) +
-                                                  2 * static_cast<int>(sizeof(TJob)))) / kAllBufs;
+                                                  2 * static_cast<int>(sizeof(TJob)))) / kTeams;
       constexpr int kMaxZero = (kMaxBuf / 16 + kTeamThreads - 1) / kTeamThreads;
 #pragma unroll
       for (int k = 0; k < kMaxZero; ++k)
@@ -512,13 +499,14 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
           PROF_ADD(8, it_t1 - it_t0)
           PROF_ADD(10, 1)
           PROF_ADD(11, cnt)
-          // kWalk == 1: the vertical weight of a tile row is the same for all 32 columns, so lane
-          // i computes it for row i (and how many source rows lie before it) once per item; the
-          // rows then take it with a shuffle instead of each lane redoing the integer walk.
+          // The vertical weight of a tile row is the same for all 32 columns, so lane i computes
+          // it for row i (and how many source rows lie before it) once per item; the rows then
+          // take it with a shuffle instead of each lane redoing the integer walk (9 % fewer
+          // instructions per launch; the time did not move: the kernel is not issue-bound).
           // Rows past the box get a NaN weight: their sample compares false.
-          [[maybe_unused]] float wl = 0.f;
-          [[maybe_unused]] unsigned advmask = 0u;
-          if (kWalk == 1) {
+          float wl;
+          unsigned advmask;
+          {
             const int t = remy + lane * step;          // < 2^24: exact in fp32
             int q = __float2int_rd(static_cast<float>(t) * invDy);
             int rem = t - q * Dy;
@@ -544,21 +532,10 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
             int sh = kAligned ? 0 : ((a0 + ra * rw15) & 15);   // row address mod 16 in HBM
 #pragma unroll
             for (int i = 0; i < kTileRows; ++i) {
-              bool adv;
-              float v;
-              if (kWalk == 1) {
-                v = fmaf(__shfl_sync(0xffffffffu, wl, i), dh, ht);
-                if (v >= thr)
-                  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + static_cast<uint32_t>(sh)), "r"(one));
-                adv = (advmask >> i) & 1u;      // warp-uniform, applied as a predicate
-              } else {
-                v = fmaf(static_cast<float>(remy) * invDy, dh, ht);
-                if (v >= thr && i < cnt)
-                  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + static_cast<uint32_t>(sh)), "r"(one));
-                remy += step;
-                adv = remy >= Dy;               // warp-uniform, applied as a predicate
-                remy = adv ? remy - Dy : remy;
-              }
+              const float v = fmaf(__shfl_sync(0xffffffffu, wl, i), dh, ht);
+              if (v >= thr)
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr + static_cast<uint32_t>(sh)), "r"(one));
+              const bool adv = (advmask >> i) & 1u;      // warp-uniform, applied as a predicate
               if (kValues) {
                 if (colvalid && i < cnt) vout[static_cast<size_t>(i) * RW] = v;
               }
@@ -652,12 +629,9 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
         if (body > 0) {
           fence_proxy_async_smem();
           bulk_s2g(g + head, s + head, static_cast<uint32_t>(body));
-          if (kBufs == 1) bulk_commit();
+          bulk_commit();
         }
       }
-      // two buffers: every row lane closes one group per tile, copy or not, so that "all but
-      // the newest group" below always means "the previous tile's copy of this lane"
-      if (kBufs == 2 && lane < kTileRows) bulk_commit();
       // ---- unaligned shapes: the <= 15 head and <= 15 tail bytes of every row, one byte per
       // lane (generic-proxy copies; the bulk copies above only read the buffer)
       if (((reinterpret_cast<uintptr_t>(g0) | RW | static_cast<unsigned>(len)) & 15u) != 0u &&
@@ -678,13 +652,8 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
       __syncwarp();
       PROF_MARK(6)
       // ---- the buffer may be re-zeroed once the bulk copies have read it
-      if (kBufs == 1) {
-        if (mine) {
-          if (more) bulk_wait_read<0>();   // this buffer is zeroed again next
-          else bulk_wait_all<0>();
-        }
-      } else if (lane < kTileRows) {
-        if (more) bulk_wait_read<1>();     // the OTHER buffer's copy (issued a tile ago) has been read
+      if (mine) {
+        if (more) bulk_wait_read<0>();
         else bulk_wait_all<0>();
       }
     } else if (more) {
@@ -699,10 +668,6 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     }
     if (!more) break;
     slot = nslot;
-    if (kBufs == 2) {   // the next tile is drawn in the other buffer
-      s_buf = (s_buf == s_buf0) ? s_buf0 + buf_bytes : s_buf0;
-      buf_addr = smem_u32(s_buf);
-    }
   }
   team_bar(bar_id, kTeamThreads);   // the decoding lane's last ticket precedes the retirement
   retire();
@@ -712,21 +677,20 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
 
 }  // namespace team
 
-template <int kTeams, int kTeamWarps, int kTileRows, bool kValues, int kWalk, int kBufs = 1>
+template <int kTeams, int kTeamWarps, int kTileRows, bool kValues>
 static int launch_team_cfg(const ExpandParams &prm, const DevInfo &dev, int want_buf, cudaStream_t st) {
   using namespace team;
   const int max_optin = dev.max_smem_optin;
-  constexpr int kAllBufs = kTeams * kBufs;
   constexpr size_t kStatic = 256 + static_cast<size_t>(kTeams) * (kCand + 48);   // static __shared__ of the kernel
   const size_t fixed = static_cast<size_t>(kTeams) * kCand * sizeof(TEntry) +
                        static_cast<size_t>(kTeams) * 2 * sizeof(TJob) +
                        static_cast<size_t>(prm.B + 1) * sizeof(int) + kStatic;
-  MRX_CHECK_SUPPORTED(fixed + static_cast<size_t>(kAllBufs) * 2048 <= static_cast<size_t>(max_optin),
+  MRX_CHECK_SUPPORTED(fixed + static_cast<size_t>(kTeams) * 2048 <= static_cast<size_t>(max_optin),
                       "mrx_mask_expand: batch of %d images does not fit the scheduler table", prm.B);
   // (the kernel's zero fill is unrolled for tile buffers of up to this size)
   constexpr int kMaxBuf = (232448 - kTeams * (kCand * static_cast<int>(sizeof(TEntry)) +
-                                              2 * static_cast<int>(sizeof(TJob)))) / kAllBufs;
-  const int avail = min(static_cast<int>((static_cast<size_t>(max_optin) - fixed) / kAllBufs), kMaxBuf) & ~127;
+                                              2 * static_cast<int>(sizeof(TJob)))) / kTeams;
+  const int avail = min(static_cast<int>((static_cast<size_t>(max_optin) - fixed) / kTeams), kMaxBuf) & ~127;
   // a tile row must hold 16 pixels of R instances (aligned shapes) / one pixel + alignment shift
   const int need = (max(16 * prm.R, prm.R + 48) * kTileRows + 127) & ~127;
   // (an entry packs the instance and its tile index into 8 bits each)
@@ -734,8 +698,8 @@ static int launch_team_cfg(const ExpandParams &prm, const DevInfo &dev, int want
   int buf = avail;
   if (want_buf > 0 && want_buf < buf) buf = want_buf & ~127;
   if (buf < need) buf = need;
-  const size_t smem = static_cast<size_t>(kAllBufs) * buf + fixed - kStatic;
-  auto kern = mask_expand_team_kernel<kTeams, kTeamWarps, kTileRows, kValues, kWalk, kBufs>;
+  const size_t smem = static_cast<size_t>(kTeams) * buf + fixed - kStatic;
+  auto kern = mask_expand_team_kernel<kTeams, kTeamWarps, kTileRows, kValues>;
   static SmemCache cache;
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(kern), &cache, dev.device,
                                    static_cast<int>(smem)))
@@ -755,39 +719,23 @@ extern "C" int mrx_debug_team_profile(long long *host_dst, int count) {
 }
 #endif
 
-// The shipped shape: 6 teams x 5 warps, 10-row tiles (profiles/README.md has the sweep).
+// The shipped shape: 6 teams x 5 warps, 10-row tiles (profiles/README.md has the sweeps).
 int launch_expand_team(const ExpandParams &prm, const DevInfo &dev, int want_buf, cudaStream_t st) {
   if (prm.mw > 30) return MRX_E_UNSUPPORTED;   // caller falls back to the generic kernel
-  if (prm.values != nullptr) return launch_team_cfg<6, 5, 10, true, MRX_DEFAULT_WALK>(prm, dev, want_buf, st);
+  if (prm.values != nullptr) return launch_team_cfg<6, 5, 10, true>(prm, dev, want_buf, st);
 #ifdef MRX_DEV
-  // development sweep: MRX_EXPAND_TEAMS="<teams>x<warps>x<rows>[w<walk>]"
-  int teams = 6, warps = 5, rows = 10, walk = MRX_DEFAULT_WALK, bufs = 1;
+  // development sweep: MRX_EXPAND_TEAMS="<teams>x<warps>x<rows>"
+  int teams = 6, warps = 5, rows = 10;
   if (const char *e = getenv("MRX_EXPAND_TEAMS")) {
-    int a = 0, b = 0, c = 0, w = MRX_DEFAULT_WALK, nb = 1;
-    if (sscanf(e, "%dx%dx%dw%db%d", &a, &b, &c, &w, &nb) >= 3) {
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%dx%dx%d", &a, &b, &c) == 3) {
       teams = a;
       warps = b;
       rows = c;
-      walk = w;
-      bufs = nb;
     }
   }
-#define MRX_TEAM2_CASE(T, W, R) \
-  if (bufs == 2 && teams == T && warps == W && rows == R) return launch_team_cfg<T, W, R, false, 1, 2>(prm, dev, want_buf, st)
-  MRX_TEAM2_CASE(3, 10, 10);
-  MRX_TEAM2_CASE(3, 8, 10);
-  MRX_TEAM2_CASE(3, 6, 10);
-  MRX_TEAM2_CASE(4, 7, 8);
-  MRX_TEAM2_CASE(4, 6, 8);
-  MRX_TEAM2_CASE(5, 6, 6);
-  MRX_TEAM2_CASE(6, 5, 5);
-  MRX_TEAM2_CASE(2, 15, 16);
-  MRX_TEAM2_CASE(2, 12, 16);
-#undef MRX_TEAM2_CASE
-#define MRX_TEAM_CASE(T, W, R)                                                                  \
-  if (teams == T && warps == W && rows == R)                                                    \
-    return walk ? launch_team_cfg<T, W, R, false, 1>(prm, dev, want_buf, st)                    \
-                : launch_team_cfg<T, W, R, false, 0>(prm, dev, want_buf, st)
+#define MRX_TEAM_CASE(T, W, R) \
+  if (teams == T && warps == W && rows == R) return launch_team_cfg<T, W, R, false>(prm, dev, want_buf, st)
   MRX_TEAM_CASE(4, 7, 16);
   MRX_TEAM_CASE(5, 5, 12);
   MRX_TEAM_CASE(5, 6, 12);
@@ -799,7 +747,7 @@ int launch_expand_team(const ExpandParams &prm, const DevInfo &dev, int want_buf
   set_error("mrx_mask_expand: MRX_EXPAND_TEAMS=%dx%dx%d is not a compiled shape", teams, warps, rows);
   return MRX_E_INVALID;
 #else
-  return launch_team_cfg<6, 5, 10, false, MRX_DEFAULT_WALK>(prm, dev, want_buf, st);
+  return launch_team_cfg<6, 5, 10, false>(prm, dev, want_buf, st);
 #endif
 }
 

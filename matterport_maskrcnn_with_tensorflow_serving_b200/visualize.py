@@ -45,25 +45,12 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-def _table_is_valid(tab, alpha):
-    """The tabulated form of the blend (mrx_composite_masks with d_lut) needs every blend to keep
-    pixel values inside 0..255: true for alpha and colours in [0, 1] (what display_instances
-    passes); anything else takes the per-pixel float64 form."""
-    oma = 1 - alpha
-    return bool(oma >= 0 and tab.size > 0 and float(tab.min()) >= 0 and
-                255 * oma + float(tab.max()) < 256)
-
-
-def _is_triple(x):
-    return len(x) == 3 and not hasattr(x[0], "__len__")
-
-
 class CompositeStage:
     """Device-side inputs of the overlay for one planned batch (images, blend table, scratch),
     staged once; `run()` launches `mrx_composite_masks` on the engine's current canvas.  Lets a
     pipeline (or a benchmark) separate the upload of the images from the kernel."""
 
-    def __init__(self, engine, images, colors, alpha=0.5, table=None):
+    def __init__(self, engine, images, colors, alpha=0.5):
         import torch
 
         N.require_cuda()
@@ -95,20 +82,13 @@ class CompositeStage:
         self.d_tab = torch.from_numpy(tab).to(dev)
         self.d_off = torch.from_numpy(offs[:B].copy()).to(dev)
         self.max_px = max(int(geom[b][0]) * int(geom[b][1]) for b in range(B))
-        use_table = _table_is_valid(tab, alpha) if table is None else bool(table)
-        if use_table and not _table_is_valid(tab, alpha):
-            raise ValueError("the tabulated blend needs alpha and colours in [0, 1]")
-        self.d_lut = torch.empty((B * engine.R * 768,), dtype=torch.uint8, device=dev) \
-            if use_table else None
 
-    def run(self, stream=None, cull=True):
+    def run(self, stream=None):
         eng = self.engine
         N.check(self.lib.mrx_composite_masks(
             _ptr(eng.d_canvas), _ptr(eng.d_canvas_off), _ptr(eng.d_counts),
             _ptr(eng.d_geom), _ptr(eng.d_boxes), _ptr(self.d_in), _ptr(self.d_off),
             _ptr(self.d_tab), C.c_double(1 - self.alpha),
-            _ptr(self.d_lut) if self.d_lut is not None else C.c_void_p(0),
-            1 if cull else 0,        # the engine's canvas: instance i is zero outside its box
             _ptr(self.d_out), eng._n_images, eng.R, C.c_longlong(self.max_px),
             N.stream_ptr(stream)), "mrx_composite_masks")
         offs, geom = self.offs, self.geom
@@ -116,18 +96,14 @@ class CompositeStage:
                 for b in range(eng._n_images)]
 
 
-def composite_batch(engine, images, colors, alpha=0.5, stream=None, table=None, cull=True):
+def composite_batch(engine, images, colors, alpha=0.5, stream=None):
     """Overlay the masks an `UnmoldEngine` holds on its device canvas (after `enqueue`).
 
     images: list of uint8 HxWx3 arrays (NumPy or CUDA tensors), one per planned image, each
     of the engine's canvas size for that image.  colors: a list of RGB triples shared by all
     images, or one such list per image.  Returns a list of uint8 HxWx3 CUDA tensors.
-    table: None = tabulate the blend when that is exact (alpha, colours in [0, 1]), else
-    evaluate it per pixel in float64; False forces the per-pixel form (same output).
-    cull: visit, per block of pixels, only the instances whose box meets it (valid because the
-    expand kernel never sets a pixel outside the box; False walks every instance -- same output).
     """
-    return CompositeStage(engine, images, colors, alpha, table=table).run(stream, cull)
+    return CompositeStage(engine, images, colors, alpha).run(stream)
 
 
 def apply_masks(image, boxes, masks, colors, alpha=0.5):
@@ -158,15 +134,11 @@ def apply_masks(image, boxes, masks, colors, alpha=0.5):
     d_boxes = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.int32)).to(dev)
     d_img = torch.from_numpy(image.astype(np.uint8, copy=False)).to(dev)
     d_out = torch.empty_like(d_img)
-    tab = blend_table(colors, alpha, n)
-    d_tab = torch.from_numpy(tab).to(dev)
-    d_lut = torch.empty((n * 768,), dtype=torch.uint8, device=dev) \
-        if _table_is_valid(tab, alpha) else None
+    d_tab = torch.from_numpy(blend_table(colors, alpha, n)).to(dev)
     N.check(lib.mrx_composite_masks(
         _ptr(d_canvas), _ptr(d_off), _ptr(d_counts), _ptr(d_geom), _ptr(d_boxes), _ptr(d_img),
-        _ptr(d_off), _ptr(d_tab), C.c_double(1 - alpha),
-        _ptr(d_lut) if d_lut is not None else C.c_void_p(0), 0,   # arbitrary masks: no box cull
-        _ptr(d_out), 1, n, C.c_longlong(H * W), N.stream_ptr(None)), "mrx_composite_masks")
+        _ptr(d_off), _ptr(d_tab), C.c_double(1 - alpha), _ptr(d_out), 1, n,
+        C.c_longlong(H * W), N.stream_ptr(None)), "mrx_composite_masks")
     return d_out.cpu().numpy()
 
 

@@ -70,12 +70,9 @@ def child(args):
     rng = np.random.default_rng(0)
     img = torch.from_numpy(synth.synth_rgb_image(rng, 1024, 1024)).cuda()
     colors = visualize.random_colors(100, rng=random.Random(0))
-    comp = {}
-    for table in (None, False):
-        for cull in (True, False):
-            st = visualize.CompositeStage(eng, [img] * args.batch, colors, 0.5, table=table)
-            med, _ = timeit(lambda: st.run(cull=cull))
-            comp[("table" if table is None else "exact") + ("+cull" if cull else "")] = round(med, 4)
+    stage = visualize.CompositeStage(eng, [img] * args.batch, colors, 0.5)
+    comp, _ = timeit(lambda: stage.run())
+    comp = round(comp, 4)
     print(json.dumps({"variant": os.environ.get("MRX_EXPAND_TEAMS", "default"),
                       "flags": os.environ.get("MRX_EXPAND_FLAGS", ""),
                       "bits_warps": os.environ.get("MRX_BITS_WARPS", "default"),

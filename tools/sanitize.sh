@@ -5,7 +5,7 @@
 #   bash tools/sanitize.sh   -> gpurun_out/sanitizer_<tool>.log
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-SEL="more_instances or every_box or no_detections or small_boxes or chunk_size or leading_unit or (packed_masks and (hw0 or hw1 or hw2 or hw7 or hw8)) or packed_batch_ragged or (rle_equals and not hw4 and not hw5) or rle_touching or all_zero_box or composite_on_device or out_of_range or (production_kernel and (small_mixed or tiny_boxes)) or identity_resize or byte_canvas_after"
+SEL="more_instances or every_box or no_detections or small_boxes or chunk_size or leading_unit or (packed_masks and (hw0 or hw1 or hw2 or hw7 or hw8)) or packed_batch_ragged or (rle_equals and not hw4 and not hw5) or rle_touching or all_zero_box or composite_on_device or out_of_range or alpha_sweep or (production_kernel and (small_mixed or tiny_boxes)) or identity_resize or byte_canvas_after"
 for tool in memcheck synccheck racecheck; do
   echo "== $tool"
   timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 \
