@@ -45,6 +45,10 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def _is_triple(x):
+    return len(x) == 3 and not hasattr(x[0], "__len__")
+
+
 class CompositeStage:
     """Device-side inputs of the overlay for one planned batch (images, blend table, scratch),
     staged once; `run()` launches `mrx_composite_masks` on the engine's current canvas.  Lets a

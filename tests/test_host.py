@@ -239,3 +239,31 @@ def test_overlay_host_logic_matches_oracle():
         with pytest.raises(N.MrxError):
             visualize.apply_masks(np.zeros((4, 4, 3), np.uint8), np.zeros((1, 4), np.int32),
                                   np.zeros((4, 4, 1), bool), cols)
+
+
+def test_no_unbound_global_names_in_the_package():
+    """Static check (the GPU paths cannot run here): every name a module loads is bound
+    somewhere in it (import, def, class, assignment, argument) or is a builtin."""
+    import ast
+    import builtins
+
+    pkg = os.path.join(ROOT, "matterport_maskrcnn_with_tensorflow_serving_b200")
+    files = [os.path.join(pkg, f) for f in sorted(os.listdir(pkg)) if f.endswith(".py")]
+    files += [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for path in files:
+        tree = ast.parse(open(path).read())
+        bound = set(dir(builtins)) | {"__file__", "__name__", "__doc__"}
+        for node in ast.walk(tree):
+            if isinstance(node, (ast.FunctionDef, ast.ClassDef, ast.AsyncFunctionDef)):
+                bound.add(node.name)
+            elif isinstance(node, ast.arg):
+                bound.add(node.arg)
+            elif isinstance(node, (ast.Import, ast.ImportFrom)):
+                for a in node.names:
+                    bound.add((a.asname or a.name).split(".")[0])
+            elif isinstance(node, ast.Name) and isinstance(node.ctx, (ast.Store, ast.Del)):
+                bound.add(node.id)
+            elif isinstance(node, ast.ExceptHandler) and node.name:
+                bound.add(node.name)
+        used = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+        assert not (used - bound), (os.path.basename(path), sorted(used - bound))
