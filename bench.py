@@ -509,17 +509,13 @@ def run_ours(args, rank, world, local_rank):
     h_det, h_msk, d_det, d_msk = upload_batch(ctx, ims)
     geoms = [make_geom(im.original_image_shape, im.image_shape, im.window) for im in ims]
 
-    # 32 KB tile buffers (instead of every byte of shared memory; same tile shape at N = 100) leave
-    # room on each SM for one small preparation CTA beside the expand CTA
-    eng = UnmoldEngine(BATCH, N_INST, (28, 28), CLASSES, chunk_bytes=args.chunk_bytes or 32768,
+    eng = UnmoldEngine(BATCH, N_INST, (28, 28), CLASSES, chunk_bytes=args.chunk_bytes,
                        ctas_per_sm=args.ctas_per_sm)
     eng.plan(geoms)
     stream = torch.cuda.current_stream()
     barrier = ctx.barrier
 
-    from matterport_maskrcnn_with_tensorflow_serving_b200.engine import PipelinedUnmolder
-
-    # ---- warm-up (serial steps: one preparation launch, one expand launch)
+    # ---- warm-up
     for _ in range(max(args.warmup, 3)):
         eng.enqueue(d_det, d_msk, stream)
     torch.cuda.synchronize()
@@ -530,47 +526,42 @@ def run_ours(args, rank, world, local_rank):
     out_bytes = eng.canvas_bytes(counts)
     algo_bytes = out_bytes + masks_per_step * (28 * 28 * 4 + 24)   # SURVEY.md 8d per-instance figure
 
-    def run_steps(n_steps, kev=None):
-        """n_steps passes of the hot path.  Pipelined form (default): the preparation of step
-        k+1 runs on a second stream under the expand of step k (engine.PipelinedUnmolder);
-        inside the region there are exactly n_steps preparations and n_steps expands."""
-        if args.serial:
-            for s in range(n_steps):
-                eng.enqueue(d_det, d_msk, stream, expand=False)
-                if kev is not None:
-                    kev[s][0].record(stream)
-                eng.enqueue_expand(stream)
-                if kev is not None:
-                    kev[s][1].record(stream)
-            return
-        for s in range(n_steps):
-            pipe.step((d_det, d_msk), kernel_events=None if kev is None else kev[s])
-        pipe.drain()
-
-    pipe = None
-    if not args.serial:
-        pipe = PipelinedUnmolder(eng, stream)
-        pipe.prime(d_det, d_msk)            # the preparation the first timed expand consumes
-        run_steps(3)
-        torch.cuda.synchronize()
-
     # ---- timed region: exactly K steps, device-timed, expand kernel timed per launch
     sampler = ClockSampler(local_rank)
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
+    import ctypes as C
+
+    from matterport_maskrcnn_with_tensorflow_serving_b200 import _native as N
+    lib = eng.lib
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    st = N.stream_ptr(stream)
     # clock sampling needs load for longer than a few ms: run the same steps untimed for
     # --load-ms first (clocks settle, nvidia-smi gets samples), keep sampling through the
     # timed region
     sampler.start()
     t_load = time.perf_counter()
     while (time.perf_counter() - t_load) * 1e3 < args.load_ms:
-        run_steps(10)
+        for _ in range(10):
+            eng.enqueue(d_det, d_msk, stream)
         torch.cuda.synchronize()
     barrier()
     ev0.record(stream)
-    run_steps(args.steps, kev)
+    for s in range(args.steps):
+        N.check(lib.mrx_unmold_prepare(P(d_det), N.MRX_F32, P(d_msk), N.MRX_F32, BATCH, N_INST, 28,
+                                       28, CLASSES, P(eng.d_geom), P(eng.d_boxes),
+                                       P(eng.d_class_ids), P(eng.d_scores), P(eng.d_src_index),
+                                       P(eng.d_counts), P(eng.d_status),
+                                       P(eng.d_tiles), P(eng.d_sched), st), "prepare")
+        kev[s][0].record(stream)
+        N.check(lib.mrx_mask_expand(P(eng.d_tiles), P(eng.d_src_index), P(eng.d_boxes),
+                                    P(eng.d_counts), P(eng.d_geom),
+                                    P(eng.d_canvas_off), P(eng.d_canvas), BATCH, N_INST, 28, 28,
+                                    eng.chunk_bytes, eng.ctas_per_sm, P(eng.d_sched), st),
+                "expand")
+        kev[s][1].record(stream)
     ev1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -580,27 +571,6 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     total_masks = ctx.sum_over_ranks(masks_per_step)
     value = total_masks * args.steps / (max_ms * 1e-3)
-
-    # ---- the same K steps strictly one after the other (no second stream), for reference
-    serial = None
-    if not args.serial:
-        sv = []
-        for _ in range(3):
-            barrier()
-            s0 = torch.cuda.Event(enable_timing=True)
-            s1 = torch.cuda.Event(enable_timing=True)
-            s0.record(stream)
-            for _s in range(args.steps):
-                eng.enqueue(d_det, d_msk, stream)
-            s1.record(stream)
-            torch.cuda.synchronize()
-            sv.append(ctx.max_over_ranks(s0.elapsed_time(s1)) / args.steps)
-        sv.sort()
-        serial = {"ms_per_step": sv[1], "value": total_masks / (sv[1] * 1e-3), "unit": UNIT,
-                  "what": "preparation and expand of each step back to back on one stream"}
-    eng.use_set(0)
-    if pipe is not None:
-        eng.use_set(pipe.cur)
 
     # ---- parity of the timed step's output: image 0 of this very batch against the oracle
     # (outside timing; rank 0; the same check tests/test_gpu_unmold.py runs exhaustively)
@@ -764,10 +734,6 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "per-step working set (813 MB in + 3.36 GB out per GPU) exceeds the "
                              "126 MB L2; no explicit flush",
                        "tile_buffer_bytes": eng.chunk_bytes or "auto", "seed": SEED,
-                       "step": ("serial" if args.serial else
-                                "pipelined: the preparation launch of step k+1 (prologue + class-tile "
-                                "gather, small CTAs, second stream) runs under the expand launch of "
-                                "step k; K preparations + K expands inside the timed region"),
                        "numa": numa},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -777,7 +743,6 @@ def run_ours(args, rank, world, local_rank):
                             "of counts, boxes and the [H,W,N] bool canvases; every batch's "
                             "masks are waited for on the host"},
             "gpu_launches": 2 * args.steps,
-            "serial": serial,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "mask_expand_team_kernel",
                          "kernel_ms": k_ms, "kernel_ms_min": float(np.min(expand_ms)),
@@ -815,9 +780,6 @@ def main():
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
-    ap.add_argument("--serial", action="store_true",
-                    help="time the steps strictly one after the other (no overlap of the next "
-                         "step's preparation with the expand kernel)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of the CPU legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

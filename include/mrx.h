@@ -117,15 +117,12 @@ int mrx_gather_tiles(const void *d_mrcnn_mask, int mask_dtype,
  * outputs as above; the class tiles are stored by ORIGINAL detection row,
  *   d_tiles[b][t] = float32(mrcnn_mask[b, t, :, :, class_id of row t])      (rows with class 0: untouched)
  * which needs nothing from the prologue, so both run side by side in the same grid.  The expand
- * entry points then take d_tile_index = d_src_index (kept instance k -> its row).
- * small_ctas: non-zero launches 128-thread CTAs capped at 32 registers, one of which fits on an
- * SM beside a resident mrx_mask_expand CTA: the preparation of the NEXT batch (its own output
- * buffers, d_sched = NULL) can then run on a second stream under the expand of the current one. */
+ * entry points then take d_tile_index = d_src_index (kept instance k -> its row). */
 int mrx_unmold_prepare(const void *d_detections, int det_dtype, const void *d_mrcnn_mask,
                        int mask_dtype, int B, int R, int mh, int mw, int C,
                        const int *d_geom, int *d_boxes, int *d_class_ids, void *d_scores,
                        int *d_src_index, int *d_counts, int *d_status,
-                       float *d_tiles, unsigned int *d_sched, int small_ctas, void *stream);
+                       float *d_tiles, unsigned int *d_sched, void *stream);
 
 /* The hot kernel.  For every image b writes the bool canvas [H_b, W_b, N_b]
  * (N innermost, 1 byte per element, values 0/1) at d_canvas + d_canvas_off[b]:

@@ -46,7 +46,7 @@ SIGNATURES = {
                                  _vp]),
     "mrx_gather_tiles": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mrx_unmold_prepare": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
-                                _vp, _vp, _vp, _vp, _i, _vp]),
+                                _vp, _vp, _vp, _vp, _vp]),
     "mrx_mask_expand": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp,
                              _vp]),
     "mrx_mask_expand_values": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,

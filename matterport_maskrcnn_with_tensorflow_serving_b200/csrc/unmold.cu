@@ -185,10 +185,9 @@ __device__ __forceinline__ double ld_strided(const double *p) {
 }
 
 // copy the `tile_elems` elements in[0], in[C], in[2C], ... to out[0 .. tile_elems) as float32
-template <typename T, int kThreads = kGatherThreads>
+template <typename T>
 __device__ __forceinline__ void gather_strided(const T *__restrict__ in, int tile_elems, int C,
-                                               float *__restrict__ out) {
-  constexpr int kGatherThreads = kThreads;   // (shadows the launch constant inside this body)  // every element is its own 32-byte sector (stride C): keep four loads in flight per thread
+                                               float *__restrict__ out) {  // every element is its own 32-byte sector (stride C): keep four loads in flight per thread
   for (int p0 = threadIdx.x; p0 < tile_elems; p0 += 4 * kGatherThreads) {
     T v[4];
 #pragma unroll
@@ -226,13 +225,8 @@ gather_tiles_kernel(const T *__restrict__ mask, int R, int tile_elems, int C,
 // tile of row t's own class -- rows with class_id == 0 can never be kept (the first of them ends
 // the list) and are skipped -- and CTA (R, b) runs the prologue of image b.  The expand kernels
 // then find instance k's tile through src_index[b][k].
-//
-// kThreads = 256: the stand-alone form.  kThreads = 128 with at most 32 registers per thread
-// (launch bound of 16 CTAs per SM): a CTA of this form fits beside a resident
-// mask_expand_team_kernel CTA (960 threads x 64 registers leave 4096 registers and 1088 threads
-// per SM), so the preparation of batch k+1 can run on a second stream UNDER the expand of batch k.
-template <typename TD, typename TM, int kThreads>
-__global__ void __launch_bounds__(kThreads, kThreads == 128 ? 16 : 6)
+template <typename TD, typename TM>
+__global__ void __launch_bounds__(kGatherThreads)
 unmold_prepare_kernel(const TD *__restrict__ det, const TM *__restrict__ mask, int R, int C,
                       int tile_elems, const int *__restrict__ geom, int *__restrict__ boxes,
                       int *__restrict__ class_ids, TD *__restrict__ scores,
@@ -241,8 +235,8 @@ unmold_prepare_kernel(const TD *__restrict__ det, const TM *__restrict__ mask, i
                       float *__restrict__ tiles) {
   const int b = blockIdx.y;
   if (static_cast<int>(blockIdx.x) == R) {
-    prologue_body<TD, kThreads>(b, det, R, C, geom, boxes, class_ids, scores, src_index, counts, status,
-                                job_counter);
+    prologue_body<TD, kGatherThreads>(b, det, R, C, geom, boxes, class_ids, scores, src_index, counts,
+                                      status, job_counter);
     return;
   }
   const int t = blockIdx.x;
@@ -250,8 +244,8 @@ unmold_prepare_kernel(const TD *__restrict__ det, const TM *__restrict__ mask, i
   if (cls == 0) return;
   if (cls < 0) cls += C;
   if (cls < 0 || cls >= C) cls = 0;    // flagged by the prologue; stay in bounds
-  gather_strided<TM, kThreads>(mask + (static_cast<size_t>(b) * R + t) * tile_elems * C + cls,
-                               tile_elems, C, tiles + (static_cast<size_t>(b) * R + t) * tile_elems);
+  gather_strided(mask + (static_cast<size_t>(b) * R + t) * tile_elems * C + cls, tile_elems, C,
+                 tiles + (static_cast<size_t>(b) * R + t) * tile_elems);
 }
 
 // =====================================================================================
@@ -643,8 +637,7 @@ extern "C" int mrx_unmold_prepare(const void *d_detections, int det_dtype, const
                                   int mask_dtype, int B, int R, int mh, int mw, int C,
                                   const int *d_geom, int *d_boxes, int *d_class_ids, void *d_scores,
                                   int *d_src_index, int *d_counts, int *d_status,
-                                  float *d_tiles, unsigned int *d_sched, int small_ctas,
-                                  void *stream) {
+                                  float *d_tiles, unsigned int *d_sched, void *stream) {
   MRX_CHECK_ARG(d_detections && d_mrcnn_mask && d_geom && d_boxes && d_class_ids && d_scores &&
                     d_src_index && d_counts && d_status && d_tiles,
                 "mrx_unmold_prepare: null pointer");
@@ -657,22 +650,16 @@ extern "C" int mrx_unmold_prepare(const void *d_detections, int det_dtype, const
   if (B == 0) return MRX_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(R + 1, B);
-#define MRX_PREPARE_T(TD, TM, THREADS)                                                           \
-  unmold_prepare_kernel<TD, TM, THREADS><<<grid, THREADS, 0, st>>>(                              \
+#define MRX_PREPARE(TD, TM)                                                                      \
+  unmold_prepare_kernel<TD, TM><<<grid, kGatherThreads, 0, st>>>(                                \
       static_cast<const TD *>(d_detections), static_cast<const TM *>(d_mrcnn_mask), R, C, mh * mw, \
       d_geom, d_boxes, d_class_ids, static_cast<TD *>(d_scores), d_src_index, d_counts, d_status,   \
       d_sched, d_tiles)
-#define MRX_PREPARE(TD, TM)                   \
-  do {                                        \
-    if (small_ctas) MRX_PREPARE_T(TD, TM, 128); \
-    else MRX_PREPARE_T(TD, TM, 256);          \
-  } while (0)
   if (det_dtype == MRX_F64 && mask_dtype == MRX_F64) MRX_PREPARE(double, double);
   else if (det_dtype == MRX_F64) MRX_PREPARE(double, float);
   else if (mask_dtype == MRX_F64) MRX_PREPARE(float, double);
   else MRX_PREPARE(float, float);
 #undef MRX_PREPARE
-#undef MRX_PREPARE_T
   MRX_LAUNCH_CHECK("unmold_prepare_kernel");
   return MRX_OK;
 }

@@ -87,10 +87,13 @@ class UnmoldEngine:
             raise ValueError(f"max_batch must be in [1, {N.MRX_MAX_BATCH}]")
         dev, i32 = self.device, torch.int32
         B, R = self.B, self.R
-        # what the preparation step writes and the expand step reads; a second set
-        # (`use_set(1)`) lets the preparation of batch k+1 run under the expand of batch k
-        self._sets = [self._new_set()]
-        self._cur = 0
+        self.d_boxes = torch.empty((B, R, 4), dtype=i32, device=dev)
+        self.d_class_ids = torch.empty((B, R), dtype=i32, device=dev)
+        self.d_scores = torch.empty((B, R), dtype=_torch_dtype(self.det_dtype), device=dev)
+        self.d_src_index = torch.empty((B, R), dtype=i32, device=dev)
+        self.d_counts = torch.zeros((B,), dtype=i32, device=dev)
+        self.d_status = torch.zeros((B,), dtype=i32, device=dev)
+        self.d_tiles = torch.empty((B, R, self.mh, self.mw), dtype=torch.float32, device=dev)
         self.d_geom = torch.zeros((B, N.MRX_GEOM_INTS), dtype=i32, device=dev)
         self.d_canvas_off = torch.zeros((B,), dtype=torch.int64, device=dev)
         # scheduler words of the expand kernels: zeroed once here, left zeroed by every launch
@@ -105,34 +108,6 @@ class UnmoldEngine:
         self.lock = threading.RLock()
         # pinned staging for fetch_meta (one D2H batch + one synchronisation per call)
         self._h_meta = None
-
-    def _new_set(self):
-        torch = _torch()
-        dev, i32, B, R = self.device, torch.int32, self.B, self.R
-        return {
-            "boxes": torch.empty((B, R, 4), dtype=i32, device=dev),
-            "class_ids": torch.empty((B, R), dtype=i32, device=dev),
-            "scores": torch.empty((B, R), dtype=_torch_dtype(self.det_dtype), device=dev),
-            "src_index": torch.empty((B, R), dtype=i32, device=dev),
-            "counts": torch.zeros((B,), dtype=i32, device=dev),
-            "status": torch.zeros((B,), dtype=i32, device=dev),
-            "tiles": torch.empty((B, R, self.mh, self.mw), dtype=torch.float32, device=dev),
-        }
-
-    def use_set(self, i):
-        """Select which of the two sets of preparation outputs (boxes, class ids, scores, kept
-        rows, counts, status, tiles) the following enqueue_* / fetch_meta calls work on."""
-        while len(self._sets) <= i:
-            self._sets.append(self._new_set())
-        self._cur = int(i)
-
-    d_boxes = property(lambda self: self._sets[self._cur]["boxes"])
-    d_class_ids = property(lambda self: self._sets[self._cur]["class_ids"])
-    d_scores = property(lambda self: self._sets[self._cur]["scores"])
-    d_src_index = property(lambda self: self._sets[self._cur]["src_index"])
-    d_counts = property(lambda self: self._sets[self._cur]["counts"])
-    d_status = property(lambda self: self._sets[self._cur]["status"])
-    d_tiles = property(lambda self: self._sets[self._cur]["tiles"])
 
     def release(self):
         """Free the canvas and the packed-output buffer (the work buffers stay)."""
@@ -179,17 +154,12 @@ class UnmoldEngine:
         self._packed_off_host = None
 
     # ------------------------------------------------------------------ launch
-    def enqueue(self, d_detections, d_mrcnn_mask, stream=None, expand=True, beside_expand=False):
+    def enqueue(self, d_detections, d_mrcnn_mask, stream=None, expand=True):
         """Enqueue the three kernels for the planned batch on `stream` (no host sync).
         d_detections [n,R,6] and d_mrcnn_mask [n,R,mh,mw,C] are device tensors of the
         dtypes given at construction (d_mrcnn_mask may also be PINNED HOST memory: the class
         gather then reads the wanted elements over PCIe instead of the whole tensor being
-        copied first).  expand=False stops after the class-tile gather.
-        beside_expand=True (with expand=False): launch the preparation as small CTAs that fit on
-        an SM beside a resident expand CTA and leave the scheduler words alone -- for running it
-        on another stream, into the other set (`use_set`), under the expand of the previous
-        batch (the engine must have been built with chunk_bytes <= 32768 so that the expand
-        kernel leaves shared memory for them)."""
+        copied first).  expand=False stops after the class-tile gather."""
         n = self._n_images
         if n == 0:
             raise RuntimeError("call plan() first")
@@ -213,8 +183,7 @@ class UnmoldEngine:
             _dtype_code(self.mask_dtype), n, self.R, self.mh, self.mw, self.C,
             _ptr(self.d_geom), _ptr(self.d_boxes), _ptr(self.d_class_ids), _ptr(self.d_scores),
             _ptr(self.d_src_index), _ptr(self.d_counts),
-            _ptr(self.d_status), _ptr(self.d_tiles),
-            C.c_void_p(0) if beside_expand else _ptr(self.d_sched), 1 if beside_expand else 0, st),
+            _ptr(self.d_status), _ptr(self.d_tiles), _ptr(self.d_sched), st),
             "mrx_unmold_prepare")
         if expand:
             self.enqueue_expand(stream)
@@ -560,70 +529,6 @@ class Molder:
             _dtype_code(out_dtype), _ptr(out), C.c_void_p(0), N.stream_ptr(stream)),
             "mrx_mold_image_batch")
         return out, window, scale, padding
-
-
-class PipelinedUnmolder:
-    """Device-resident stream of batches of one plan: while the expand kernel of batch k writes
-    the canvas, the preparation of batch k+1 (steps 1-6 + class-tile gather, 8 % of a serial
-    step) runs on a second stream as small CTAs that fit on the SMs beside the expand CTAs, into
-    the engine's other set of preparation outputs.  The engine must leave shared memory for
-    them: build it with `chunk_bytes=32768` (the expand kernel then takes 32 KB tile buffers
-    instead of every byte of shared memory; same tile shape at N = 100).
-
-        pipe = PipelinedUnmolder(engine)
-        pipe.prime(d_det0, d_msk0)                  # preparation of the first batch
-        for k in range(K):
-            pipe.step(next_batch_or_None)           # expand(k), then preparation(k+1) under it
-            # batch k's canvas is complete once `pipe.expand_done[k % 2]` has fired
-    """
-
-    def __init__(self, engine, stream=None):
-        torch = _torch()
-        if not (0 < engine.chunk_bytes <= 32768):
-            raise ValueError("PipelinedUnmolder needs an engine built with 0 < chunk_bytes <= 32768")
-        self.eng = engine
-        self.main = stream or torch.cuda.current_stream(engine.device)
-        self.side = torch.cuda.Stream(device=engine.device)
-        self.prep_done = [torch.cuda.Event(), torch.cuda.Event()]
-        self.expand_done = [torch.cuda.Event(), torch.cuda.Event()]
-        self._expanded = [False, False]
-        self.cur = 0
-        engine.use_set(1)
-        engine.use_set(0)
-
-    def prime(self, d_det, d_msk):
-        eng = self.eng
-        eng.use_set(self.cur)
-        eng.enqueue(d_det, d_msk, self.main, expand=False)
-        self.prep_done[self.cur].record(self.main)
-
-    def step(self, next_inputs=None, canvas_ptr=None, kernel_events=None):
-        """Expand the prepared batch on the main stream; then start the preparation of
-        `next_inputs` = (d_det, d_msk) under it on the side stream.  kernel_events: optional
-        (before, after) timing events recorded around the expand launch."""
-        eng, cur, other = self.eng, self.cur, self.cur ^ 1
-        self.main.wait_event(self.prep_done[cur])
-        eng.use_set(cur)
-        if kernel_events is not None:
-            kernel_events[0].record(self.main)
-        eng.enqueue_expand(self.main, canvas_ptr=canvas_ptr)      # launched FIRST: takes its SMs
-        if kernel_events is not None:
-            kernel_events[1].record(self.main)
-        self.expand_done[cur].record(self.main)
-        self._expanded[cur] = True
-        if next_inputs is not None:
-            if self._expanded[other]:
-                self.side.wait_event(self.expand_done[other])     # its last reader has finished
-            eng.use_set(other)
-            eng.enqueue(next_inputs[0], next_inputs[1], self.side, expand=False, beside_expand=True)
-            self.prep_done[other].record(self.side)
-            self.cur = other
-        eng.use_set(cur)
-        return cur
-
-    def drain(self):
-        """Make the main stream wait for the preparation still running on the side stream."""
-        self.main.wait_event(self.prep_done[self.cur])
 
 
 class StreamingUnmolder:

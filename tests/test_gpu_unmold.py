@@ -442,47 +442,3 @@ def test_streaming_unmolder_pipeline(cuda_device):
             H, W = im.original_image_shape[:2]
             m = out[off:off + H * W * n].numpy().reshape(H, W, n).view(np.bool_)
             assert compare_masks(m, rm, rz, rb)[0] == 0
-
-
-def test_pipelined_unmolder_matches_serial_steps(cuda_device):
-    """engine.PipelinedUnmolder: the preparation of batch k+1 runs on a second stream under the
-    expand of batch k, into the engine's other set of buffers.  Four different batches through
-    the pipeline give, batch by batch, the bytes the plain serial call gives."""
-    import torch
-
-    from matterport_maskrcnn_with_tensorflow_serving_b200.engine import PipelinedUnmolder
-
-    hw, R, n_img = (200, 264), 20, 3
-    batches = [synth.make_batch(500 + k, n_img, hw, (0, 20), num_classes=5, max_instances=R)
-               for k in range(4)]
-    geoms = [make_geom(im.original_image_shape, im.image_shape, im.window) for im in batches[0]]
-    dev_in = [(torch.from_numpy(np.stack([im.detections for im in ims])).cuda(),
-               torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()) for ims in batches]
-    ref_eng = UnmoldEngine(n_img, R, (28, 28), 5)
-    ref_eng.plan(geoms)
-    want = []
-    for d_det, d_msk in dev_in:
-        ref_eng.enqueue(d_det, d_msk)
-        counts, boxes, cls, scores = ref_eng.fetch_meta()
-        total = int(ref_eng._offsets[n_img])
-        want.append((counts.copy(), boxes.copy(), ref_eng.d_canvas[:total].clone()))
-    eng = UnmoldEngine(n_img, R, (28, 28), 5, chunk_bytes=32768)
-    eng.plan(geoms)
-    with pytest.raises(ValueError):
-        PipelinedUnmolder(ref_eng)                      # built without shared-memory headroom
-    pipe = PipelinedUnmolder(eng)
-    pipe.prime(*dev_in[0])
-    for rep in range(3):                                # several rounds over the four batches
-        for k in range(4):
-            nxt = dev_in[(k + 1) % 4]
-            pipe.step(nxt)
-            counts, boxes, cls, scores = eng.fetch_meta()      # synchronises the main stream
-            wc, wb, wcanvas = want[k]
-            assert np.array_equal(counts, wc)
-            for b in range(n_img):
-                assert np.array_equal(boxes[b, :wc[b]], wb[b, :wc[b]])
-                o = int(eng._offsets[b])
-                n = hw[0] * hw[1] * int(wc[b])
-                assert torch.equal(eng.d_canvas[o:o + n], wcanvas[o:o + n]), (rep, k, b)
-    pipe.drain()
-    torch.cuda.synchronize()

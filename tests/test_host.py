@@ -49,7 +49,7 @@ def test_host_side_argument_validation():
                                       p16, None) == -2      # mask tiles wider than 30 columns
     assert b"30" in lib.mrx_last_error()
     assert lib.mrx_unmold_prepare(p16, 0, p16, 3, 1, 100, 28, 28, 81, p16, p16, p16, p16, p16,
-                                  p16, p16, p16, p16, 0, None) == -1   # bad mask dtype
+                                  p16, p16, p16, p16, None) == -1      # bad mask dtype
     assert lib.mrx_peer_export(None, None) == -1 and lib.mrx_peer_wait(None, 1, 1, None) == -1
 
 
