@@ -1,5 +1,6 @@
-"""Developer tool: per-phase cycle totals of the team kernel (build with
-MRX_NVCC_FLAGS=-DMRX_TEAM_PROFILE).  Prints mean cycles per tile for warp 0 of a team and for
+"""Developer tool: per-phase cycle totals of the team kernel.  Build and run:
+    MRX_NVCC_FLAGS="-DMRX_DEV -DMRX_TEAM_PROFILE" MRX_LIB_NAME=libmrx_prof.so python -m matterport_maskrcnn_with_tensorflow_serving_b200.build
+    MRX_LIB=libmrx_prof.so MRX_EXPAND_TEAMS=6x5x10 python tools/team_profile.py  Prints mean cycles per tile for warp 0 of a team and for
 the other warps."""
 import ctypes
 import os
@@ -12,9 +13,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from matterport_maskrcnn_with_tensorflow_serving_b200 import synth, _native  # noqa: E402
 from matterport_maskrcnn_with_tensorflow_serving_b200.engine import UnmoldEngine, make_geom  # noqa: E402
 
-teams, warps, rows = [int(v) for v in os.environ.get("MRX_EXPAND_TEAMS", "4x7x16").split("x")]
-base = synth.make_batch(123, 4, (1024, 1024), 100, num_classes=81)
-ims = [base[i % 4] for i in range(32)]
+teams, warps, rows = [int(v) for v in os.environ.get("MRX_EXPAND_TEAMS", "6x5x10").split("x")]
+ims = synth.make_batch(20260921, 32, (1024, 1024), 100, num_classes=81)
 d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
 d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
 eng = UnmoldEngine(32, 100, (28, 28), 81)
