@@ -56,6 +56,10 @@ def unmold_case(name, batch, hw, n, classes, R, iters, base_images=4, seed=7, co
     pk_ms, _ = time_ms(lambda: eng.enqueue_expand_packed(), iters)
     pack_ms, _ = time_ms(lambda: eng.pack_masks(), iters)
     pro_ms, _ = time_ms(lambda: eng.enqueue(d_det, d_msk, expand=False), iters)
+    # COCO RLE from the tiles (count pass, one host read of the totals, write pass)
+    rle_ms, _ = time_ms(lambda: eng.enqueue_rle(), max(3, iters // 4))
+    d_runs, off = eng.enqueue_rle()
+    rle_bytes = int(d_runs.numel()) * 4
     if composite:
         import random
 
@@ -78,6 +82,7 @@ def unmold_case(name, batch, hw, n, classes, R, iters, base_images=4, seed=7, co
                       "prologue_plus_class_gather_ms": round(pro_ms, 4),
                       "expand_packed_ms": round(pk_ms, 4),
                       "expand_packed_Mmasks_per_s": round(masks / pk_ms / 1e3, 2),
+                      "rle_ms_incl_host_read": round(rle_ms, 4), "rle_output_MB": round(rle_bytes / 1e6, 2),
                       "pack_kernel_ms": round(pack_ms, 4),
                       "pack_kernel_canvas_read_GBps": round(out_bytes / pack_ms / 1e6, 1)}), flush=True)
     del eng, d_det, d_msk
