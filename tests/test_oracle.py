@@ -213,3 +213,39 @@ def test_composite_golden():
     out = oracle.composite_instances(c["image"], g["boxes"], masks, colors, alpha=0.5)
     assert np.array_equal(out, c["overlay"])
     assert (out != c["image"]).any()
+
+
+def _rle_by_loop(mask):
+    """Independent restatement of pycocotools' rleEncode: walk the pixels in column-major order
+    and count (plain Python loop, small masks only)."""
+    h, w = mask.shape
+    counts, prev, run = [], 0, 0
+    for x in range(w):
+        for y in range(h):
+            v = int(mask[y, x])
+            if v != prev:
+                counts.append(run)
+                run, prev = 0, v
+            run += 1
+    counts.append(run)
+    return counts
+
+
+def test_rle_known_answers_and_roundtrip():
+    """COCO 'uncompressed RLE': column-major runs, starting with zeros."""
+    m = np.array([[0, 1], [1, 1]], dtype=bool)            # column-major: 0 1 | 1 1
+    assert oracle.rle_encode(m)["counts"].tolist() == [1, 3]
+    assert oracle.rle_encode(np.ones((3, 2), bool))["counts"].tolist() == [0, 6]
+    assert oracle.rle_encode(np.zeros((3, 2), bool))["counts"].tolist() == [6]
+    m = np.zeros((4, 3), bool)
+    m[3, 0] = m[0, 1] = True                               # run crosses the column seam
+    assert oracle.rle_encode(m)["counts"].tolist() == [3, 2, 7]
+    rng = np.random.default_rng(12)
+    for shape in [(1, 1), (5, 7), (16, 3), (9, 31)]:
+        for p in (0.1, 0.5, 0.9):
+            m = rng.random(shape) < p
+            r = oracle.rle_encode(m)
+            assert r["size"] == list(shape) and int(r["counts"].sum()) == m.size
+            assert r["counts"].tolist() == _rle_by_loop(m)
+            assert np.array_equal(oracle.rle_decode(r), m)
+            assert (r["counts"][1:] > 0).all()             # only the first run may be empty
