@@ -616,14 +616,10 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     PROF_MARK(4)
     const int nslot = slot ^ 1;
     const bool more = s_job[nslot].valid != 0;
-    const int len = pw * N;
-    // unaligned shapes: the <= 15 head and <= 15 tail bytes of every row do not go out with the
-    // bulk copies
-    const bool ragged = ((reinterpret_cast<uintptr_t>(g0) | RW | static_cast<unsigned>(len)) & 15u) != 0u &&
-                        !MRX_FLAG(p, 0x400);
     if (wt == 0) {
       // ---- store the tile: lane r owns the bulk copy of row r (its 16-byte aligned body)
       const bool mine = lane < kk;
+      const int len = pw * N;
       if (mine && !MRX_FLAG(p, 0x400)) {
         unsigned char *g = g0 + static_cast<size_t>(lane) * RW;
         const int a = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15u);
@@ -636,18 +632,10 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
           bulk_commit();
         }
       }
-      __syncwarp();
-      PROF_MARK(6)
-      // ---- the buffer may be re-zeroed once the bulk copies have read it
-      if (mine) {
-        if (more) bulk_wait_read<0>();
-        else bulk_wait_all<0>();
-      }
-    } else if (wt == kTeamWarps - 1) {
-      if (ragged) {
-        // ---- head and tail bytes of every row, one byte per lane (generic-proxy copies beside
-        // warp 0's bulk copies, which only read the buffer; this warp is otherwise idle but for
-        // one lane's decode, and keeping warp 0 free of it shortens the drain)
+      // ---- unaligned shapes: the <= 15 head and <= 15 tail bytes of every row, one byte per
+      // lane (generic-proxy copies; the bulk copies above only read the buffer)
+      if (((reinterpret_cast<uintptr_t>(g0) | RW | static_cast<unsigned>(len)) & 15u) != 0u &&
+          !MRX_FLAG(p, 0x400)) {
         for (int r = 0; r < kk; ++r) {
           unsigned char *g = g0 + static_cast<size_t>(r) * RW;
           const int a = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15u);
@@ -661,14 +649,20 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
           }
         }
       }
-      if (more) {
+      __syncwarp();
+      PROF_MARK(6)
+      // ---- the buffer may be re-zeroed once the bulk copies have read it
+      if (mine) {
+        if (more) bulk_wait_read<0>();
+        else bulk_wait_all<0>();
+      }
+    } else if (more) {
+      if (wt == kTeamWarps - 1) {
         // ---- the descriptor of this tile retires: decode the tile after next into it
         if (lane == 0) decode(static_cast<int>(atomicAdd(p.job_counter, 1u)), cur_b, &s_job[slot]);
         __syncwarp();
         PROF_MARK(7)
-      }
-    } else if (more) {
-      {
+      } else {
         cull(s_job[nslot], nslot, 0, wt - 1, kTeamWarps - 2);
       }
     }
