@@ -104,19 +104,25 @@ pack_quads_kernel(const unsigned char *__restrict__ canvas, const long long *__r
   }
 }
 
+// A fixed number of CTAs walks every image: an image packed by pack_quads_kernel (N % 4 == 0)
+// costs each CTA one test, not one empty CTA per 256 pixels.
 __global__ void __launch_bounds__(kPackThreads)
 pack_bytes_kernel(const unsigned char *__restrict__ canvas, const long long *__restrict__ canvas_off,
                   const int *__restrict__ counts, const int *__restrict__ geom,
-                  unsigned char *__restrict__ packed, const long long *__restrict__ packed_off) {
+                  unsigned char *__restrict__ packed, const long long *__restrict__ packed_off,
+                  int B) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int b = blockIdx.z;
-  const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
-  const int y = blockIdx.y;
-  const int x0 = blockIdx.x * kPackPixels;
-  const int N = counts[b];
-  if (y >= H || x0 >= W || N <= 0 || (N & 3) == 0) return;   // N % 4 == 0: pack_quads_kernel
-  const int npx = min(kPackPixels, W - x0);
   const int t = threadIdx.x;
+  for (int b = 0; b < B; ++b) {
+  const int N = counts[b];
+  if (N <= 0 || (N & 3) == 0) continue;   // N % 4 == 0: pack_quads_kernel
+  const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
+  const int xblocks = (W + kPackPixels - 1) / kPackPixels;
+  for (int job = blockIdx.x; job < H * xblocks; job += gridDim.x) {
+  const int y = job / xblocks;
+  const int x0 = (job - y * xblocks) * kPackPixels;
+  const int npx = min(kPackPixels, W - x0);
+  __syncthreads();   // the previous job's readers are done with the staging buffer
 
   // ---- stage the npx * N bytes of these pixels at their global address mod 16
   const unsigned char *src = canvas + canvas_off[b] + (static_cast<long long>(y) * W + x0) * N;
@@ -164,6 +170,8 @@ pack_bytes_kernel(const unsigned char *__restrict__ canvas, const long long *__r
     }
     dst[g + static_cast<long long>(n) * plane] = static_cast<unsigned char>(acc);
   }
+  }   // jobs of image b
+  }   // images
 }
 
 }  // namespace mrx
@@ -200,9 +208,10 @@ extern "C" int mrx_pack_masks(const unsigned char *d_canvas, const long long *d_
                                                      d_packed, d_packed_off);
     MRX_LAUNCH_CHECK("pack_quads_kernel");
   }
-  dim3 grid((max_w + kPackPixels - 1) / kPackPixels, max_h, B);
-  pack_bytes_kernel<<<grid, kPackThreads, smem, st>>>(d_canvas, d_canvas_off, d_counts, d_geom,
-                                                      d_packed, d_packed_off);
+  int occ = 0;
+  MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pack_bytes_kernel, kPackThreads, smem));
+  pack_bytes_kernel<<<dev.sms * max(occ, 1), kPackThreads, smem, st>>>(d_canvas, d_canvas_off, d_counts,
+                                                                    d_geom, d_packed, d_packed_off, B);
   MRX_LAUNCH_CHECK("pack_bytes_kernel");
   return MRX_OK;
 }

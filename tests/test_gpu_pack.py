@@ -97,3 +97,55 @@ def test_byte_canvas_after_a_canvasless_plan(cuda_device):
     b, c, s, m = api_utils.unmold_detections(*item_of(big, np.float32))
     assert m.shape == (300, 260, b.shape[0])
     assert np.array_equal(packed, np.packbits(m.transpose(2, 0, 1), axis=-1))
+
+
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("upload", ["copy", "zero_copy", "hybrid"])
+def test_streaming_unmolder_modes(cuda_device, packed, upload):
+    """engine.StreamingUnmolder over three streams: every combination of output layout (byte
+    canvas / bit-packed) and mask upload (copied, read in place from pinned memory, half and
+    half) returns, batch after batch, the bytes the plain engine produces."""
+    import torch
+
+    from matterport_maskrcnn_with_tensorflow_serving_b200.engine import (StreamingUnmolder, UnmoldEngine,
+                                                                         make_geom)
+
+    n_img, R, hw = 5, 12, (96, 136)
+    batches = [synth.make_batch(700 + k, n_img, hw, (0, 12), num_classes=6, max_instances=R)
+               for k in range(4)]
+    geoms = [make_geom(im.original_image_shape, im.image_shape, im.window) for im in batches[0]]
+    ref = UnmoldEngine(n_img, R, (28, 28), 6)
+    ref.plan(geoms)
+    want = []
+    for ims in batches:
+        d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
+        d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
+        ref.enqueue(d_det, d_msk)
+        if packed:
+            d_out, off = ref.enqueue_expand_packed()
+            total = int(off[-1])
+        else:
+            d_out, total = ref.d_canvas, int(ref._offsets[n_img])
+        counts, boxes, _, _ = ref.fetch_meta()
+        want.append((counts.copy(), d_out[:total].cpu().clone(), ref.packed_layout()[0] if packed else ref._offsets))
+    eng = UnmoldEngine(n_img, R, (28, 28), 6)
+    sm = StreamingUnmolder(eng, geoms, packed=packed, mask_upload=upload)
+    pinned = [(torch.from_numpy(np.stack([im.detections for im in ims])).pin_memory(),
+               torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).pin_memory()) for ims in batches]
+    got = {}
+    for k, (h_det, h_msk) in enumerate(pinned):
+        sm.submit(h_det, h_msk)
+        if k:
+            c, b, o = sm.wait(k - 1)
+            got[k - 1] = (c.clone(), o.clone())
+    c, b, o = sm.wait(len(pinned) - 1)
+    got[len(pinned) - 1] = (c.clone(), o.clone())
+    H, W = hw
+    for k in range(4):
+        wc, wout, woff = want[k]
+        gc, gout = got[k]
+        assert np.array_equal(gc.numpy(), wc)
+        for i in range(n_img):
+            nb = int(wc[i]) * H * ((W + 7) // 8) if packed else H * W * int(wc[i])
+            lo = int(woff[i])
+            assert torch.equal(gout[lo:lo + nb], wout[lo:lo + nb]), (k, i)
