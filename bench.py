@@ -656,8 +656,7 @@ def run_ours(args, rank, world, local_rank):
             "kernel": "mask_expand_bits_kernel", "kernel_ms": pk_k_med, "kernel_ms_best": pk_k_best,
             "output_bytes_per_step": int(pk_total),
         }
-        for name, kw in (("e2e", {}), ("e2e_zero_copy_masks", {"mask_upload": "zero_copy"}),
-                         ("e2e_hybrid_masks", {"mask_upload": "hybrid"})):
+        for name, kw in (("e2e", {}), ("e2e_zero_copy_masks", {"mask_upload": "zero_copy"})):
             smp = StreamingUnmolder(eng, geoms, packed=True, **kw)
             sec, (pc, pb, po) = run_e2e(smp, e2e_steps)
             assert int(pc.sum()) == masks_per_step
@@ -670,10 +669,6 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.empty_cache()
         packed["e2e"]["path"] = ("StreamingUnmolder(packed=True): pinned inputs -> H2D -> prologue, "
                                  "class gather, packed expand -> D2H of the packed masks")
-        packed["e2e_hybrid_masks"]["path"] = (
-            "same, half of the images' mask tensors copied by the copy engine, the other half read in "
-            "place by the gather kernel (balances the H2D copy against the small reads that share the "
-            "upstream direction with the D2H)")
         packed["e2e_zero_copy_masks"]["path"] = (
             "same, but mrcnn_mask (99.7 % of the input bytes, 81 classes of which one per instance "
             "is used) is never copied: the class-gather kernel reads the wanted floats from the "

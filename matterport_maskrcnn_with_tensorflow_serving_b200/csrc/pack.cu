@@ -113,14 +113,20 @@ pack_bytes_kernel(const unsigned char *__restrict__ canvas, const long long *__r
                   int B) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int t = threadIdx.x;
+  // jobs (256 pixels of one row) are numbered across all the images this kernel packs and dealt
+  // round robin to the CTAs: no per-image tail
+  int base = 0;
+  int job = blockIdx.x;
   for (int b = 0; b < B; ++b) {
   const int N = counts[b];
   if (N <= 0 || (N & 3) == 0) continue;   // N % 4 == 0: pack_quads_kernel
   const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
   const int xblocks = (W + kPackPixels - 1) / kPackPixels;
-  for (int job = blockIdx.x; job < H * xblocks; job += gridDim.x) {
-  const int y = job / xblocks;
-  const int x0 = (job - y * xblocks) * kPackPixels;
+  const int njobs = H * xblocks;
+  for (; job < base + njobs; job += gridDim.x) {
+  const int local = job - base;
+  const int y = local / xblocks;
+  const int x0 = (local - y * xblocks) * kPackPixels;
   const int npx = min(kPackPixels, W - x0);
   __syncthreads();   // the previous job's readers are done with the staging buffer
 
@@ -171,6 +177,7 @@ pack_bytes_kernel(const unsigned char *__restrict__ canvas, const long long *__r
     dst[g + static_cast<long long>(n) * plane] = static_cast<unsigned char>(acc);
   }
   }   // jobs of image b
+  base += njobs;
   }   // images
 }
 

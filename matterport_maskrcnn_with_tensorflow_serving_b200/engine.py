@@ -154,22 +154,15 @@ class UnmoldEngine:
         self._packed_off_host = None
 
     # ------------------------------------------------------------------ launch
-    def enqueue(self, d_detections, d_mrcnn_mask, stream=None, expand=True, images=None):
-        """Enqueue the kernels for the planned batch on `stream` (no host sync).
+    def enqueue(self, d_detections, d_mrcnn_mask, stream=None, expand=True):
+        """Enqueue the three kernels for the planned batch on `stream` (no host sync).
         d_detections [n,R,6] and d_mrcnn_mask [n,R,mh,mw,C] are device tensors of the
         dtypes given at construction (d_mrcnn_mask may also be PINNED HOST memory: the class
         gather then reads the wanted elements over PCIe instead of the whole tensor being
-        copied first).  expand=False stops after the class-tile gather.
-        images=(b0, b1) (with expand=False): prepare only that range of the planned batch; the
-        tensors passed are then the inputs of THOSE images ([b1-b0, ...])."""
-        b0, b1 = (0, self._n_images) if images is None else images
-        n = b1 - b0
-        if self._n_images == 0:
+        copied first).  expand=False stops after the class-tile gather."""
+        n = self._n_images
+        if n == 0:
             raise RuntimeError("call plan() first")
-        if images is not None and expand:
-            raise ValueError("images= prepares a sub-range; run the expand step separately")
-        if n <= 0:
-            return
         torch = _torch()
         if tuple(d_detections.shape) != (n, self.R, 6) or \
                 d_detections.dtype != _torch_dtype(self.det_dtype):
@@ -188,9 +181,9 @@ class UnmoldEngine:
         N.check(self.lib.mrx_unmold_prepare(
             _ptr(d_detections), _dtype_code(self.det_dtype), _ptr(d_mrcnn_mask),
             _dtype_code(self.mask_dtype), n, self.R, self.mh, self.mw, self.C,
-            _ptr(self.d_geom[b0:]), _ptr(self.d_boxes[b0:]), _ptr(self.d_class_ids[b0:]),
-            _ptr(self.d_scores[b0:]), _ptr(self.d_src_index[b0:]), _ptr(self.d_counts[b0:]),
-            _ptr(self.d_status[b0:]), _ptr(self.d_tiles[b0:]), _ptr(self.d_sched), st),
+            _ptr(self.d_geom), _ptr(self.d_boxes), _ptr(self.d_class_ids), _ptr(self.d_scores),
+            _ptr(self.d_src_index), _ptr(self.d_counts),
+            _ptr(self.d_status), _ptr(self.d_tiles), _ptr(self.d_sched), st),
             "mrx_unmold_prepare")
         if expand:
             self.enqueue_expand(stream)
@@ -555,30 +548,24 @@ class StreamingUnmolder:
 
     mask_upload="zero_copy": `mrcnn_mask` is not copied to the device at all -- the class-tile
     gather kernel reads the 1/C of it that is needed straight from the pinned host buffer over
-    PCIe (detections are still copied: 2.4 KB per image).
-    mask_upload="hybrid": the first half of the images' mask tensors is copied by the copy engine
-    (large transfers, which overlap the download of the previous batch's results) while the
-    gather kernel reads the second half's wanted elements in place -- the small reads share the
-    upstream direction with the download, so splitting the work balances the two."""
+    PCIe (detections are still copied: 2.4 KB per image)."""
 
     def __init__(self, engine, geoms, packed=False, mask_upload="copy"):
         torch = _torch()
-        if mask_upload not in ("copy", "zero_copy", "hybrid"):
-            raise ValueError("mask_upload: 'copy', 'zero_copy' or 'hybrid'")
+        if mask_upload not in ("copy", "zero_copy"):
+            raise ValueError("mask_upload: 'copy' or 'zero_copy'")
         self.eng = engine
         self.packed = bool(packed)
         self.zero_copy = mask_upload == "zero_copy"
-        self.n_copied = None      # images whose mask tensor is copied (the rest is read in place)
         engine.plan(geoms, canvas=False)       # the outputs live here, double-buffered
         n = engine._n_images
         self.n = n
         dev = engine.device
         det_t, msk_t = _torch_dtype(engine.det_dtype), _torch_dtype(engine.mask_dtype)
         self.d_det = [torch.empty((n, engine.R, 6), dtype=det_t, device=dev) for _ in range(2)]
-        self.n_copied = 0 if self.zero_copy else (n // 2 if mask_upload == "hybrid" else n)
-        self.d_msk = None if self.n_copied == 0 else [
-            torch.empty((self.n_copied, engine.R, engine.mh, engine.mw, engine.C), dtype=msk_t,
-                        device=dev) for _ in range(2)]
+        self.d_msk = None if self.zero_copy else [
+            torch.empty((n, engine.R, engine.mh, engine.mw, engine.C), dtype=msk_t, device=dev)
+            for _ in range(2)]
         self.total = engine.packed_layout()[1] if self.packed else int(engine._offsets[n])
         self.d_out = [torch.empty((self.total,), dtype=torch.uint8, device=dev) for _ in range(2)]
         self.h_out = [torch.empty((self.total,), dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -596,11 +583,11 @@ class StreamingUnmolder:
         self.out_free = [torch.cuda.Event() for _ in range(2)]
         self.out_done = {}
         self.k = 0
-        img_bytes = engine.R * engine.mh * engine.mw * engine.C * engine.mask_dtype.itemsize
+        msk_bytes = n * engine.R * engine.mh * engine.mw * engine.C * engine.mask_dtype.itemsize
         self.h2d_bytes = self.d_det[0].numel() * self.d_det[0].element_size() + \
-            self.n_copied * img_bytes
-        # in place: the gather kernel pulls one 32-byte sector per wanted element over PCIe
-        self.pcie_read_bytes = (n - self.n_copied) * engine.R * engine.mh * engine.mw * 32
+            (0 if self.zero_copy else msk_bytes)
+        # zero copy: the gather kernel pulls one 32-byte sector per wanted element over PCIe
+        self.pcie_read_bytes = n * engine.R * engine.mh * engine.mw * 32 if self.zero_copy else 0
         self.d2h_bytes = self.total + 4 * (n + 4 * n * engine.R)
 
     def submit(self, h_det, h_msk):
@@ -609,25 +596,21 @@ class StreamingUnmolder:
         torch = _torch()
         k, i = self.k, self.k % 2
         eng = self.eng
-        nc = self.n_copied
-        if nc < self.n and not h_msk.is_pinned():
-            raise ValueError("reading masks in place needs the mask tensor in pinned host memory")
+        if self.zero_copy and not h_msk.is_pinned():
+            raise ValueError("zero_copy needs the mask tensor in pinned host memory")
         with torch.cuda.stream(self.in_stream):
             if k >= 2:
                 self.in_stream.wait_event(self.in_free[i])     # kernels of batch k-2 read d_*[i]
             self.d_det[i].copy_(h_det, non_blocking=True)
-            if nc:
-                self.d_msk[i].copy_(h_msk[:nc], non_blocking=True)
+            if not self.zero_copy:
+                self.d_msk[i].copy_(h_msk, non_blocking=True)
             self.h2d_done[i].record(self.in_stream)
         ms = self.main_stream
         ms.wait_event(self.h2d_done[i])
         if k >= 2:
             ms.wait_event(self.out_free[i])                    # download of batch k-2 read d_out[i]
-        if nc == self.n or nc == 0:
-            eng.enqueue(self.d_det[i], self.d_msk[i] if nc else h_msk, ms, expand=False)
-        else:     # copied images from the device tensor, the rest in place from the host
-            eng.enqueue(self.d_det[i][:nc], self.d_msk[i], ms, expand=False, images=(0, nc))
-            eng.enqueue(self.d_det[i][nc:], h_msk[nc:], ms, expand=False, images=(nc, self.n))
+        msk = h_msk if self.zero_copy else self.d_msk[i]
+        eng.enqueue(self.d_det[i], msk, ms, expand=False)
         if self.packed:
             eng.enqueue_expand_packed(ms, packed_ptr=self.d_out[i].data_ptr())
         else:

@@ -100,11 +100,10 @@ def test_byte_canvas_after_a_canvasless_plan(cuda_device):
 
 
 @pytest.mark.parametrize("packed", [False, True])
-@pytest.mark.parametrize("upload", ["copy", "zero_copy", "hybrid"])
+@pytest.mark.parametrize("upload", ["copy", "zero_copy"])
 def test_streaming_unmolder_modes(cuda_device, packed, upload):
     """engine.StreamingUnmolder over three streams: every combination of output layout (byte
-    canvas / bit-packed) and mask upload (copied, read in place from pinned memory, half and
-    half) returns, batch after batch, the bytes the plain engine produces."""
+    canvas / bit-packed) and mask upload (copied, or read in place from pinned memory) returns, batch after batch, the bytes the plain engine produces."""
     import torch
 
     from matterport_maskrcnn_with_tensorflow_serving_b200.engine import (StreamingUnmolder, UnmoldEngine,
