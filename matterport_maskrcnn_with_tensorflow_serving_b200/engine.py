@@ -12,7 +12,6 @@ every computation on the path is a libmrx kernel launched through ctypes.
 from __future__ import annotations
 
 import ctypes as C
-import sys
 import threading
 
 import numpy as np

@@ -9,7 +9,6 @@ CUDA path identical inputs.  It has no dependency on the oracle or on the GPU.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 
 import numpy as np

@@ -2,7 +2,6 @@
 import numpy as np
 
 import oracle
-from matterport_maskrcnn_with_tensorflow_serving_b200 import synth
 
 # Stated fp32 tolerance of the resized (pre-threshold) mask values: the reference
 # interpolates in float64 (inputs are widened float32, serve.py:131-136); the device does

@@ -24,9 +24,14 @@ from matterport_maskrcnn_with_tensorflow_serving_b200.model_configs import MaskR
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--coco", action="store_true",
+                help="BASELINE configs[2] instead: 800x1333 images, 1-100 instances each")
 args = ap.parse_args()
 torch.cuda.set_device(0)
-ims = bench.make_bench_images(0, args.batch)
+if args.coco:
+    ims = synth.make_batch(7, args.batch, (800, 1333), (1, 100), num_classes=81)
+else:
+    ims = bench.make_bench_images(0, args.batch)
 d_det = torch.from_numpy(np.stack([im.detections for im in ims])).cuda()
 d_msk = torch.from_numpy(np.stack([im.mrcnn_mask for im in ims])).cuda()
 eng = UnmoldEngine(args.batch, 100, (28, 28), 81)
@@ -38,7 +43,7 @@ big = synth.synth_rgb_image(rng, 1080, 1920)
 d_big = torch.from_numpy(big).cuda()
 srcs = [torch.from_numpy(synth.synth_rgb_image(rng, *hw)).cuda()
         for hw in [(1024, 1024), (800, 1333), (2160, 3840)]]
-img = torch.from_numpy(synth.synth_rgb_image(rng, 1024, 1024)).cuda()
+img = torch.from_numpy(synth.synth_rgb_image(rng, *ims[0].original_image_shape[:2])).cuda()
 colors = visualize.random_colors(100, rng=random.Random(0))
 for _ in range(2):
     eng.enqueue(d_det, d_msk)
