@@ -85,6 +85,14 @@ struct __align__(16) TJob {
 
 // Tile geometry of an image: tile width in pixels and the shared-memory row pitch.
 // `rowcap` = buffer bytes / tile rows (a multiple of 16).
+// A warp draws 32 columns at a time, so a tile is a whole number of 32-column blocks -- plus a
+// last partial block when that adds at least half a block: at N = 55 a row holds 62 pixels, and
+// 32 + 30 columns fill the buffer (and amortise the per-tile costs) twice as well as 32 alone.
+__device__ __forceinline__ int whole_blocks(int p) {
+  if (p < 32) return p;
+  return (p & 31) >= 16 ? p : (p & ~31);
+}
+
 __device__ __forceinline__ void tile_geom(int W, int N, int rowcap, int &P, int &pitch) {
   const unsigned RW = static_cast<unsigned>(W) * N;
   if ((RW & 15u) == 0u) {
@@ -92,7 +100,7 @@ __device__ __forceinline__ void tile_geom(int W, int N, int rowcap, int &P, int 
     const int m = 16 / (((N | 16) & -(N | 16)));   // lowest set bit of N|16 == gcd(N,16)
     int p = (rowcap / N) / m * m;
     if (p > kMaxP) p = kMaxP;   // a multiple of 16, hence of m
-    if (p >= 32) p &= ~31;      // whole 32-column blocks (a warp draws 32 columns at a time)
+    p = whole_blocks(p);        // (stays a multiple of m: m divides 16 and 32)
     if (p < m) p = m;           // the host checks 16 * R * kTileRows <= buffer
     if (p >= W) p = W;
     P = p;
@@ -100,7 +108,7 @@ __device__ __forceinline__ void tile_geom(int W, int N, int rowcap, int &P, int 
   } else {
     int p = (rowcap - 32) / N;
     if (p > kMaxP) p = kMaxP;
-    if (p >= 32) p &= ~31;      // whole 32-column blocks
+    p = whole_blocks(p);
     if (p < 1) p = 1;
     if (p >= W) p = W;
     P = p;
