@@ -9,21 +9,25 @@
 // device -> host copy of the masks for callers that only want the overlay.
 //
 // Alternatives measured this round and removed again (profiles/README.md): tabulating the blend
-// per (instance, channel, value) instead of evaluating it in fp64 per pixel (0.884 vs 0.885 ms)
-// and restricting every block of pixels to the instances whose box meets it (0.947 ms: slower);
-// the kernel is bound by the stage-then-walk structure (global-load latency), not by the blend.
+// per (instance, channel, value) instead of evaluating it in fp64 per pixel (0.884 vs 0.885 ms),
+// restricting every block of pixels to the instances whose box meets it (0.947 ms: slower), and
+// persistent CTAs with a two-stage bulk-copy ring (0.96 ms: four resident CTAs per SM are too
+// few threads for the divergent walk; time went as 1/CTAs).  What did pay: replacing the
+// load-and-store staging loop by ONE bulk copy per block (0.886 -> 0.653 ms).
 //
 // HBM-read bound: N bytes of canvas per pixel (3.36 GB per config-2 batch) + 3 B in + 3 B out.
 // One CTA = 256 consecutive pixels of one image: their 256*N canvas bytes are contiguous
-// (N innermost) and are staged into shared memory with 16-byte loads; thread t then walks
-// pixel t's N bytes (4 at a time when N % 4 == 0: most words are zero) and applies the
-// blends of the set instances in instance order -- fp64 with explicit _rn intrinsics in
-// NumPy's operation order, truncation to uint32 after every instance: bit-exact.
+// (N innermost) and are brought into shared memory by a single 1-D bulk copy (TMA, completion
+// on an mbarrier) issued by thread 0 while the CTA loads its blend constants; eight CTAs are
+// resident per SM, so ~200 KB of copies are in flight per SM.  Thread t then walks pixel t's
+// N bytes (4 at a time when N % 4 == 0: most words are zero) and applies the blends of the set
+// instances in instance order -- fp64 with explicit _rn intrinsics in NumPy's operation
+// order, truncation to uint32 after every instance: bit-exact.
 #include "common.cuh"
 
 namespace mrx {
 
-constexpr int kCompThreads = 256;
+constexpr int kCompThreads = 256;   // 128: 0.688 ms, 384/512: 0.667 ms, 256: 0.653 ms
 
 __global__ void __launch_bounds__(kCompThreads)
 composite_masks_kernel(const unsigned char *__restrict__ canvas,
@@ -48,36 +52,33 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   unsigned char *s_skip = smem + ((static_cast<size_t>(R) * 3 * sizeof(double) + 15) & ~static_cast<size_t>(15));
   unsigned char *s_can = s_skip + ((R + 15) & ~15);
 
+  // 256*N is a multiple of 16 and so is every canvas slot offset; the slot holds
+  // round_up(H*W*N, 16) bytes, so the copy of the last block may take its pad bytes.  One 1-D
+  // bulk copy (TMA) brings the block's canvas bytes in while the constants below are loaded.
+  __shared__ __align__(8) uint64_t s_bar;
+  const unsigned bytes = (static_cast<unsigned>(npx) * N + 15u) & ~15u;
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+    if (bytes) {
+      mbar_arrive_expect_tx(&s_bar, bytes);
+      bulk_g2s(s_can, canvas + canvas_off[b] + static_cast<size_t>(p0) * N, bytes, &s_bar);
+    } else {
+      mbar_arrive(&s_bar);
+    }
+  }
   for (int i = t; i < N * 3; i += kCompThreads)
     s_blend[i] = blend[static_cast<size_t>(b) * R * 3 + i];
   for (int i = t; i < N; i += kCompThreads) {
     const int4 bx = boxes[static_cast<size_t>(b) * R + i];
     s_skip[i] = (bx.x | bx.y | bx.z | bx.w) == 0;   // upstream: `if not np.any(boxes[i]): continue`
   }
-  if (N > 0) {
-    // 256*N is a multiple of 16 and so is every canvas slot offset: whole uint4 loads; the
-    // slot holds round_up(H*W*N, 16) bytes, so the last block may read its pad bytes
-    const unsigned char *src = canvas + canvas_off[b] + static_cast<size_t>(p0) * N;
-    const int n16 = (npx * N + 15) >> 4;
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
-    uint4 *d4 = reinterpret_cast<uint4 *>(s_can);
-    // four independent 16-byte loads in flight per thread
-    int i = t;
-    for (; i + 3 * kCompThreads < n16; i += 4 * kCompThreads) {
-      const uint4 a0 = __ldg(s4 + i), a1 = __ldg(s4 + i + kCompThreads),
-                  a2 = __ldg(s4 + i + 2 * kCompThreads), a3 = __ldg(s4 + i + 3 * kCompThreads);
-      d4[i] = a0;
-      d4[i + kCompThreads] = a1;
-      d4[i + 2 * kCompThreads] = a2;
-      d4[i + 3 * kCompThreads] = a3;
-    }
-    for (; i < n16; i += kCompThreads) d4[i] = __ldg(s4 + i);
-  }
   __syncthreads();
   if (t >= npx) return;
 
   const unsigned char *ip = images + image_off[b] + static_cast<size_t>(p0 + t) * 3;
   unsigned v0 = ip[0], v1 = ip[1], v2 = ip[2];
+  mbar_wait(&s_bar, 0);
   auto apply = [&](int i) {
     if (s_skip[i]) return;
     const double *bl = s_blend + i * 3;
