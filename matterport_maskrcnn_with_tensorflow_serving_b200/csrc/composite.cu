@@ -60,6 +60,9 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
   if (t == 0) {
     mbar_init(&s_bar, 1);
     fence_mbar_init();
+  }
+  if (t < 32) __syncwarp();
+  if (t == 0) {
     if (bytes) {
       mbar_arrive_expect_tx(&s_bar, bytes);
       bulk_g2s(s_can, canvas + canvas_off[b] + static_cast<size_t>(p0) * N, bytes, &s_bar);

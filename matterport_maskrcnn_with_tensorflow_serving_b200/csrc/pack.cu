@@ -9,37 +9,162 @@
 //
 // HBM-read bound: N bytes per pixel in, N/8 out.  Two kernels, each image goes to one of them:
 //
-// pack_quads_kernel (N % 4 == 0, e.g. the full 100 instances): no shared memory at all.  A thread
-// owns 32 consecutive pixels x 4 consecutive instances: thirty-two independent 4-byte loads
-// (the 0/1 bytes of its four instances at each pixel), folded with
+// pack_quads_kernel (N % 4 == 0, e.g. the full 100 instances).  A thread owns 32 consecutive
+// pixels x 4 consecutive instances: thirty-two 4-byte loads (the 0/1 bytes of its four instances
+// at each pixel), folded with
 //     acc[b] |= (word & 0x01010101) << (7 - k)        pixel 8*b + k of the thread's 32
 // into one output byte per (8 pixels, instance), transposed with eight byte permutes into one
-// 32-bit word per instance plane and stored.  Lanes are laid out 4 pixel runs x 8 instance
-// quads, so every load instruction of a warp reads four fully used 32-byte sectors and every
-// store writes 16 contiguous bytes per plane.  (A first version staged 256 pixels in shared
-// memory and re-read them: 2 x 25.6 KB of shared-memory traffic per 25.6 KB of canvas put it at
-// the shared-memory bandwidth, 0.42 of the HBM roofline.)
+// 32-bit word per instance plane and stored.  Two forms, chosen per image:
+//   staged (up to ~220 instance slots): the CTA's 256 pixels arrive as eight 1-D bulk copies
+//     (TMA) and the loads are conflict-free shared-memory loads -- 0.545 ms on the config-2
+//     batch, 6.9 TB/s of reads + writes (above the measured COPY peak: the kernel reads 8 bytes
+//     for each it writes);
+//   direct (more slots than that): the loads go to global memory, lanes laid out 4 pixel runs x
+//     8 quads so that every load instruction reads four fully used 32-byte sectors -- 0.76 ms on
+//     the same batch (5.9 sectors per request: latency of many small loads).
+// (Round 1 staged with ordinary loads and stores: 2 x 25.6 KB of shared-memory traffic per
+// 25.6 KB of canvas put it at the shared-memory bandwidth, 0.42 of the HBM roofline.)
 //
 // pack_bytes_kernel (any N, any alignment; ragged instance counts): 256 consecutive pixels of a
-// row staged in shared memory at their global address mod 16, then one instance per lane slot.
+// row staged in shared memory at their global address mod 16 (one bulk copy), then one instance
+// per lane slot.
 #include "common.cuh"
 
 namespace mrx {
 
 constexpr int kPackThreads = 256;
 constexpr int kPackPixels = 256;
+constexpr int kPackRuns = kPackPixels / 32;   // runs of 32 pixels per CTA (staged form)
+
+// Bytes between two staged runs of 32 pixels x N instances: room for the run at any offset
+// 0..15 plus the word after its last byte, and 16 mod 128 -- consecutive runs start four banks
+// apart.
+__host__ __device__ inline int pack_run_pitch(int N) { return ((32 * N + 35 + 127) & ~127) + 16; }
 
 __global__ void __launch_bounds__(kPackThreads)
 pack_quads_kernel(const unsigned char *__restrict__ canvas, const long long *__restrict__ canvas_off,
                   const int *__restrict__ counts, const int *__restrict__ geom,
-                  unsigned char *__restrict__ packed, const long long *__restrict__ packed_off) {
+                  unsigned char *__restrict__ packed, const long long *__restrict__ packed_off,
+                  int stage_bytes) {
+  extern __shared__ __align__(128) unsigned char stage[];
   const int b = blockIdx.z;
   const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
   const int y = blockIdx.y;
   const int N = counts[b];
-  if (y >= H || N <= 0 || (N & 3) != 0) return;   // other N: pack_bytes_kernel
+  if (y >= H || N <= 0) return;
+  const int nquads = (N + 3) >> 2;                   // the last quad may hold 1-3 instances
+  const int wb = (W + 7) >> 3;
+  const long long plane = static_cast<long long>(H) * wb;
+
+  // acc[bq] byte j = packed byte bq of instance 4q + j  ->  word of instance j = bytes 0..3,
+  // stored to the four planes
+  auto emit = [&](const uint32_t (&acc)[4], int q, int x0) {
+    const int nv = min(4, N - 4 * q);                // instances of this quad
+    const uint32_t t0 = __byte_perm(acc[0], acc[1], 0x5140), t1 = __byte_perm(acc[2], acc[3], 0x5140);
+    const uint32_t t2 = __byte_perm(acc[0], acc[1], 0x7362), t3 = __byte_perm(acc[2], acc[3], 0x7362);
+    const uint32_t out[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632),
+                             __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
+    unsigned char *dst = packed + packed_off[b] + (static_cast<long long>(4 * q) * H + y) * wb + (x0 >> 3);
+    const int nb = min(4, wb - (x0 >> 3));           // bytes of this run inside the packed row
+    const bool word_ok = nb == 4 && ((reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(plane)) & 3u) == 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nv) break;
+      unsigned char *o = dst + j * plane;
+      if (word_ok) {
+        *reinterpret_cast<uint32_t *>(o) = out[j];
+      } else {
+        for (int t = 0; t < nb; ++t) o[t] = static_cast<unsigned char>(out[j] >> (8 * t));
+      }
+    }
+  };
+
+  // ---- staged form (whenever eight runs of 32 pixels fit the shared memory given): the CTA's
+  // 256 pixels come in as eight 1-D bulk copies (TMA), one per run, each from the run's address
+  // rounded down to 16 bytes (the offset `a` is the same for all eight: 32*N is a multiple of
+  // 16) and each run 32*N + 16 bytes further than the last, so that the eight runs of one
+  // instance quad sit in eight different banks.  Thread u owns (run u % 8, quad u / 8):
+  // conflict-free 4-byte shared loads, and the eight lanes of a quad store 32 contiguous bytes
+  // of each of its four planes.
+  const int run_pitch = pack_run_pitch(N);
+  if (kPackRuns * run_pitch <= stage_bytes) {
+    const int x_block = blockIdx.x * kPackPixels;
+    if (x_block >= W) return;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int npx_block = min(kPackPixels, W - x_block);
+    const unsigned char *src = canvas + canvas_off[b] + (static_cast<long long>(y) * W + x_block) * N;
+    const int a = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);   // multiple of 4
+    if (threadIdx.x < 32) {
+      if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+      }
+      __syncwarp();
+      const int r = threadIdx.x;
+      const int npx_r = r < kPackRuns ? max(0, min(32, npx_block - 32 * r)) : 0;
+      // whole 16-byte words: a run may take up to 15 bytes of its neighbours or of the slot's
+      // padding (every slot starts 16-byte aligned and holds whole words, see mrx.h), never
+      // unmapped memory
+      const unsigned bytes = npx_r ? (static_cast<unsigned>(a + npx_r * N) + 15u) & ~15u : 0u;
+      unsigned total = bytes;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (r == 0) mbar_arrive_expect_tx(&s_bar, total);
+      __syncwarp();
+      if (bytes)
+        bulk_g2s(stage + r * run_pitch, src + static_cast<long long>(32 * r) * N - a, bytes, &s_bar);
+    }
+    __syncthreads();   // the barrier is initialised
+    mbar_wait(&s_bar, 0);
+    for (int u = threadIdx.x; u < kPackRuns * nquads; u += kPackThreads) {
+      const int r = u & (kPackRuns - 1), q = u / kPackRuns;
+      const int npx = min(32, npx_block - 32 * r);
+      if (npx <= 0) continue;
+      const unsigned o0 = static_cast<unsigned>(r * run_pitch + a + 4 * q);
+      uint32_t acc[4];
+      if (((a | N) & 3) == 0) {
+        // every (pixel, quad) word is 4-byte aligned
+        const unsigned char *sp = stage + o0;
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) {
+          uint32_t v = 0u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int px = 8 * bq + k;
+            const uint32_t w = (npx == 32 || px < npx)
+                                   ? *reinterpret_cast<const uint32_t *>(sp + px * N) : 0u;
+            v |= (w & 0x01010101u) << (7 - k);
+          }
+          acc[bq] = v;
+        }
+      } else {
+        // any N, any alignment: the quad's four bytes straddle two words
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) {
+          uint32_t v = 0u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int px = 8 * bq + k;
+            uint32_t w = 0u;
+            if (npx == 32 || px < npx) {
+              const unsigned o = o0 + static_cast<unsigned>(px * N);
+              const uint32_t *wp = reinterpret_cast<const uint32_t *>(stage + (o & ~3u));
+              w = __funnelshift_r(wp[0], wp[1], o << 3);   // (shift taken mod 32)
+            }
+            v |= (w & 0x01010101u) << (7 - k);
+          }
+          acc[bq] = v;
+        }
+      }
+      emit(acc, q, x_block + 32 * r);
+    }
+    return;
+  }
+
+  // ---- direct form (very many instances: the runs do not fit): no shared memory, N % 4 == 0
+  // only (other N: pack_bytes_kernel)
+  if ((N & 3) != 0) return;
   const int lane = threadIdx.x & 31;
-  const int nquads = N >> 2;
   const int qblocks = (nquads + 7) >> 3;             // 8 instance quads per warp
   const int pblocks = (W + 127) >> 7;                // 4 runs of 32 pixels per warp
   const int wid = blockIdx.x * (kPackThreads / 32) + (threadIdx.x >> 5);
@@ -83,25 +208,7 @@ pack_quads_kernel(const unsigned char *__restrict__ canvas, const long long *__r
       acc[bq] = a;
     }
   }
-  // acc[bq] byte j = packed byte bq of instance 4q + j  ->  word of instance j = bytes 0..3
-  const uint32_t t0 = __byte_perm(acc[0], acc[1], 0x5140), t1 = __byte_perm(acc[2], acc[3], 0x5140);
-  const uint32_t t2 = __byte_perm(acc[0], acc[1], 0x7362), t3 = __byte_perm(acc[2], acc[3], 0x7362);
-  const uint32_t out[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632),
-                           __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
-  const int wb = (W + 7) >> 3;
-  const long long plane = static_cast<long long>(H) * wb;
-  unsigned char *dst = packed + packed_off[b] + (static_cast<long long>(4 * q) * H + y) * wb + (x0 >> 3);
-  const int nb = min(4, wb - (x0 >> 3));             // bytes of this run inside the packed row
-  const bool word_ok = nb == 4 && ((reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(plane)) & 3u) == 0u;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    unsigned char *o = dst + j * plane;
-    if (word_ok) {
-      *reinterpret_cast<uint32_t *>(o) = out[j];
-    } else {
-      for (int t = 0; t < nb; ++t) o[t] = static_cast<unsigned char>(out[j] >> (8 * t));
-    }
-  }
+  emit(acc, q, x0);
 }
 
 // A fixed number of CTAs walks every image: an image packed by pack_quads_kernel (N % 4 == 0)
@@ -110,16 +217,24 @@ __global__ void __launch_bounds__(kPackThreads)
 pack_bytes_kernel(const unsigned char *__restrict__ canvas, const long long *__restrict__ canvas_off,
                   const int *__restrict__ counts, const int *__restrict__ geom,
                   unsigned char *__restrict__ packed, const long long *__restrict__ packed_off,
-                  int B) {
+                  int B, int stage_bytes) {
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_bar;
   const int t = threadIdx.x;
+  if (t == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  unsigned phase = 0u;
   // jobs (256 pixels of one row) are numbered across all the images this kernel packs and dealt
   // round robin to the CTAs: no per-image tail
   int base = 0;
   int job = blockIdx.x;
   for (int b = 0; b < B; ++b) {
   const int N = counts[b];
-  if (N <= 0 || (N & 3) == 0) continue;   // N % 4 == 0: pack_quads_kernel
+  // pack_quads_kernel has taken every image whose runs fit its staging buffer or N % 4 == 0
+  if (N <= 0 || (N & 3) == 0 || kPackRuns * pack_run_pitch(N) <= stage_bytes) continue;
   const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
   const int xblocks = (W + kPackPixels - 1) / kPackPixels;
   const int njobs = H * xblocks;
@@ -130,28 +245,20 @@ pack_bytes_kernel(const unsigned char *__restrict__ canvas, const long long *__r
   const int npx = min(kPackPixels, W - x0);
   __syncthreads();   // the previous job's readers are done with the staging buffer
 
-  // ---- stage the npx * N bytes of these pixels at their global address mod 16
+  // ---- stage the npx * N bytes of these pixels at their global address mod 16: one 1-D bulk
+  // copy (TMA) of whole 16-byte words
   const unsigned char *src = canvas + canvas_off[b] + (static_cast<long long>(y) * W + x0) * N;
   const int nbytes = npx * N;
   const int a = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
-  {
+  if (t == 0) {
     // every canvas slot starts 16-byte aligned and holds whole 16-byte words (see mrx.h): the
     // first and last word of the run may include neighbouring pixels' bytes, never unmapped memory
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(src - a);
-    uint4 *d4 = reinterpret_cast<uint4 *>(smem);
-    const int n16 = (a + nbytes + 15) >> 4;
-    int i = t;
-    for (; i + 3 * kPackThreads < n16; i += 4 * kPackThreads) {
-      const uint4 v0 = __ldg(s4 + i), v1 = __ldg(s4 + i + kPackThreads),
-                  v2 = __ldg(s4 + i + 2 * kPackThreads), v3 = __ldg(s4 + i + 3 * kPackThreads);
-      d4[i] = v0;
-      d4[i + kPackThreads] = v1;
-      d4[i + 2 * kPackThreads] = v2;
-      d4[i + 3 * kPackThreads] = v3;
-    }
-    for (; i < n16; i += kPackThreads) d4[i] = __ldg(s4 + i);
+    const unsigned n16 = static_cast<unsigned>(a + nbytes + 15) >> 4;
+    mbar_arrive_expect_tx(&s_bar, n16 * 16u);
+    bulk_g2s(smem, src - a, n16 * 16u, &s_bar);
   }
-  __syncthreads();
+  mbar_wait(&s_bar, phase);
+  phase ^= 1u;
   const unsigned char *px0 = smem + a;   // byte of (pixel x0, instance 0)
 
   const int wb = (W + 7) >> 3;                        // bytes per packed row
@@ -196,29 +303,43 @@ extern "C" int mrx_pack_masks(const unsigned char *d_canvas, const long long *d_
   MRX_CHECK_SUPPORTED(max_h <= 65535, "mrx_pack_masks: image taller than 65535 rows");
   DevInfo dev;
   if (int rc = current_device_info(&dev)) return rc;
-  const size_t smem = static_cast<size_t>(kPackPixels) * R + 32;
-  MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(dev.max_smem_optin),
-                      "mrx_pack_masks: R=%d needs %zu B of shared memory (limit %d)", R, smem,
-                      dev.max_smem_optin);
-  static SmemCache cache;
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(pack_bytes_kernel), &cache,
-                                   dev.device, static_cast<int>(smem)))
-    return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // each image is packed by exactly one of the two kernels (N % 4 == 0 or not); the other one's
-  // CTAs for that image return at once
+  // pack_quads_kernel's staged form takes every image while eight runs of R instance slots fit
+  // the shared memory of a quarter of an SM (four or more CTAs resident); beyond that, its direct
+  // form packs the images with N % 4 == 0 and pack_bytes_kernel the others
+  int stage_bytes = kPackRuns * pack_run_pitch(R);
+  if (stage_bytes + 1024 > dev.max_smem_optin / 4) stage_bytes = 0;
   {
     const int max_quads = (R + 3) >> 2;
     const int warps_per_row = ((max_w + 127) >> 7) * ((max_quads + 7) >> 3);
-    dim3 grid((warps_per_row + kPackThreads / 32 - 1) / (kPackThreads / 32), max_h, B);
-    pack_quads_kernel<<<grid, kPackThreads, 0, st>>>(d_canvas, d_canvas_off, d_counts, d_geom,
-                                                     d_packed, d_packed_off);
+    // the grid covers both forms: one CTA per 256 pixels (staged) / per eight warps' worth of
+    // (pixel run, quad) blocks (direct)
+    const int direct_ctas = (warps_per_row + kPackThreads / 32 - 1) / (kPackThreads / 32);
+    const int staged_ctas = (max_w + kPackPixels - 1) / kPackPixels;
+    static SmemCache quads_cache;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(pack_quads_kernel), &quads_cache,
+                                     dev.device, stage_bytes))
+      return rc;
+    dim3 grid(stage_bytes ? staged_ctas : direct_ctas, max_h, B);
+    pack_quads_kernel<<<grid, kPackThreads, stage_bytes, st>>>(d_canvas, d_canvas_off, d_counts,
+                                                               d_geom, d_packed, d_packed_off,
+                                                               stage_bytes);
     MRX_LAUNCH_CHECK("pack_quads_kernel");
   }
-  int occ = 0;
-  MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pack_bytes_kernel, kPackThreads, smem));
-  pack_bytes_kernel<<<dev.sms * max(occ, 1), kPackThreads, smem, st>>>(d_canvas, d_canvas_off, d_counts,
-                                                                    d_geom, d_packed, d_packed_off, B);
-  MRX_LAUNCH_CHECK("pack_bytes_kernel");
+  if (stage_bytes == 0) {
+    const size_t smem = static_cast<size_t>(kPackPixels) * R + 32;
+    MRX_CHECK_SUPPORTED(smem <= static_cast<size_t>(dev.max_smem_optin),
+                        "mrx_pack_masks: R=%d needs %zu B of shared memory (limit %d)", R, smem,
+                        dev.max_smem_optin);
+    static SmemCache cache;
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void *>(pack_bytes_kernel), &cache,
+                                     dev.device, static_cast<int>(smem)))
+      return rc;
+    int occ = 0;
+    MRX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pack_bytes_kernel, kPackThreads, smem));
+    pack_bytes_kernel<<<dev.sms * max(occ, 1), kPackThreads, smem, st>>>(
+        d_canvas, d_canvas_off, d_counts, d_geom, d_packed, d_packed_off, B, stage_bytes);
+    MRX_LAUNCH_CHECK("pack_bytes_kernel");
+  }
   return MRX_OK;
 }

@@ -14,7 +14,14 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("hw,n,R", [((96, 128), 12, 16), ((75, 333), 37, 40), ((64, 21), 5, 8),
                                     ((40, 260), 0, 4), ((300, 517), 100, 100),
                                     ((1024, 1024), 100, 100), ((800, 1333), 61, 100),
-                                    ((33, 1000), 7, 8), ((17, 9), 3, 4)])
+                                    ((33, 1000), 7, 8), ((17, 9), 3, 4),
+                                    # pack kernel, N % 4 == 0, staged form: ragged last block,
+                                    # tiny image, odd width, rows not 16-byte aligned; and the
+                                    # direct form (224 slots do not fit the staging buffer) and
+                                    # pack_bytes_kernel (226: N % 4 != 0 there)
+                                    ((37, 1000), 100, 100), ((21, 36), 8, 8), ((50, 1333), 16, 16),
+                                    ((30, 1100), 100, 100), ((44, 1333), 100, 100),
+                                    ((120, 300), 224, 224), ((120, 300), 226, 226)])
 def test_packed_masks_equal_packbits(cuda_device, hw, n, R, direct):
     """Both producers of the packed layout -- the expand kernel that writes bits directly
     (mrx_mask_expand_packed) and the pack kernel over a byte canvas (mrx_pack_masks) -- must give
