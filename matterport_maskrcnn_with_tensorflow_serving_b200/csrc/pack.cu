@@ -36,10 +36,20 @@ constexpr int kPackThreads = 256;
 constexpr int kPackPixels = 256;
 constexpr int kPackRuns = kPackPixels / 32;   // runs of 32 pixels per CTA (staged form)
 
-// Bytes between two staged runs of 32 pixels x N instances: room for the run at any offset
-// 0..15 plus the word after its last byte, and 16 mod 128 -- consecutive runs start four banks
-// apart.
-__host__ __device__ inline int pack_run_pitch(int N) { return ((32 * N + 35 + 127) & ~127) + 16; }
+// Bytes between two staged runs of 32 pixels x N instances: 16 mod 128, so that consecutive
+// runs start four banks apart, and room for the run at its offset a = address mod 16 -- N % 4
+// == 0: a <= 12 and aligned words only, 32*N + 16 is enough; other N: the highest word touched
+// ends at a + 32*N + 6.
+__host__ __device__ inline int pack_run_pitch(int N) {
+  return (N & 3) == 0 ? 32 * N + 16 : ((32 * N + 22 - 16 + 127) & ~127) + 16;
+}
+// ... and the largest such pitch over 1..R instances (the pitch is not monotonic in N)
+inline int pack_max_run_pitch(int R) {
+  int m = 0;
+  for (int n = R > 3 ? R - 3 : 1; n <= R; ++n) m = pack_run_pitch(n) > m ? pack_run_pitch(n) : m;
+  return m;
+}
+
 
 __global__ void __launch_bounds__(kPackThreads)
 pack_quads_kernel(const unsigned char *__restrict__ canvas, const long long *__restrict__ canvas_off,
@@ -307,7 +317,7 @@ extern "C" int mrx_pack_masks(const unsigned char *d_canvas, const long long *d_
   // pack_quads_kernel's staged form takes every image while eight runs of R instance slots fit
   // the shared memory of a quarter of an SM (four or more CTAs resident); beyond that, its direct
   // form packs the images with N % 4 == 0 and pack_bytes_kernel the others
-  int stage_bytes = kPackRuns * pack_run_pitch(R);
+  int stage_bytes = kPackRuns * pack_max_run_pitch(R);
   if (stage_bytes + 1024 > dev.max_smem_optin / 4) stage_bytes = 0;
   {
     const int max_quads = (R + 3) >> 2;

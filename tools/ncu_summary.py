@@ -30,7 +30,11 @@ def main():
             print(f"{h:75s} {u:12s} {v}")
     rows = page(rep, "source")
     hdr = rows[1]
-    data = rows[2:]
+    data = []
+    for r in rows[2:]:   # a report with several launches repeats the table: first launch only
+        if len(r) < len(hdr) or not r[hdr.index('# Samples')].isdigit():
+            break
+        data.append(r)
     isrc = hdr.index('Source'); isamp = hdr.index('# Samples'); iinst = hdr.index('Instructions Executed')
     tot_s = sum(int(r[isamp]) for r in data); tot_i = sum(int(r[iinst]) for r in data)
     print('total samples', tot_s, 'total warp-inst', tot_i)
