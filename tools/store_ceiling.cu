@@ -35,6 +35,9 @@ struct P {
   int jobs;
   int nb;               // chunk buffers per warp
   int zero;             // re-zero the buffer after each store
+  int delay;            // clocks of pretend compute per job (spin) before the store
+  int order;            // 0: atomic ticket, 1: static round robin (job = worker + k * workers)
+  int jitter;           // delay varies per job: uniform in [delay - jitter, delay + jitter] (hash of the job)
   unsigned int *counter;
 };
 
@@ -48,10 +51,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) store_kernel(const P p) {
     reinterpret_cast<uint4 *>(mine)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
   int k = 0;
+  const int worker = blockIdx.x * kWarps + warp, workers = gridDim.x * kWarps;
   while (true) {
     int j = 0;
-    if (lane == 0) j = static_cast<int>(atomicAdd(p.counter, 1u));
-    j = __shfl_sync(0xffffffffu, j, 0);
+    if (p.order == 1) {
+      j = worker + k * workers;
+    } else {
+      if (lane == 0) j = static_cast<int>(atomicAdd(p.counter, 1u));
+      j = __shfl_sync(0xffffffffu, j, 0);
+    }
     if (j >= p.jobs) break;
     unsigned char *buf = mine + static_cast<size_t>(k % p.nb) * job_bytes;
     // the store issued nb jobs ago from this buffer must have been read out
@@ -67,6 +75,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) store_kernel(const P p) {
         reinterpret_cast<uint4 *>(buf)[i] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
+    if (p.delay) {
+      long long d = p.delay;
+      if (p.jitter) {
+        unsigned h = static_cast<unsigned>(j) * 2654435761u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        d += static_cast<long long>(h % static_cast<unsigned>(2 * p.jitter + 1)) - p.jitter;
+      }
+      const long long t0 = clock64();
+      while (clock64() - t0 < d) {}
+      __syncwarp();
+    }
     if (lane == 0) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       const int band = j / p.segs_per_row, sg = j % p.segs_per_row;
@@ -113,7 +132,57 @@ static float run(P p, int sms, int iters) {
   return best;
 }
 
-int main() {
+template <int kWarps>
+static void grid_row(P p, int sms, const char *tag) {
+  const float t = run<kWarps>(p, sms, 5);
+  printf("  %d warps %.4f ms (%.0f GB/s)", kWarps, t, t > 0 ? p.total / t / 1e6 : 0.f);
+}
+
+// focused grid for the team kernel's pattern: 3200-byte row segments, zero-fill per job, one
+// buffer per stream; streams per SM x rows per job x pretend-compute x claim order
+static int team_grid(unsigned char *dst, unsigned int *counter, int sms, long long total, long long RW) {
+  const int rows_list[] = {8, 10, 12, 16, 20};
+  const int delays[] = {0, 3000, 8000};
+  for (int order = 0; order <= 1; ++order)
+    for (int delay : delays)
+      for (int rows : rows_list) {
+        P p;
+        p.dst = dst; p.total = total; p.seg = 3200; p.rows = rows; p.row_stride = RW;
+        p.segs_per_row = static_cast<int>(RW / 3200);
+        p.band_bytes = rows * RW;
+        p.jobs = static_cast<int>((1024 / rows) * 32 * (RW / 3200));   // whole bands only
+        p.total = static_cast<long long>(p.jobs) * 3200 * rows;
+        p.nb = 1; p.zero = 1; p.delay = delay; p.order = order; p.jitter = 0; p.counter = counter;
+        // bands of one image follow each other; images are 1024 rows apart
+        printf("order %d delay %5d rows %2d :", order, delay, rows);
+        grid_row<2>(p, sms, ""); grid_row<3>(p, sms, ""); grid_row<4>(p, sms, "");
+        grid_row<5>(p, sms, ""); grid_row<6>(p, sms, ""); grid_row<8>(p, sms, "");
+        printf("\n");
+      }
+  return 0;
+}
+
+static int jitter_grid(unsigned char *dst, unsigned int *counter, int sms, long long total, long long RW) {
+  const int delays[] = {3000, 4000, 5000, 5800, 6500};
+  const int jitters[] = {0, 1, 2};   // 0: none, 1: +-50 %, 2: +-90 %
+  for (int delay : delays)
+    for (int jm : jitters) {
+      P p;
+      p.dst = dst; p.seg = 3200; p.rows = 10; p.row_stride = RW;
+      p.segs_per_row = static_cast<int>(RW / 3200);
+      p.band_bytes = p.rows * RW;
+      p.jobs = static_cast<int>((1024 / p.rows) * 32 * (RW / 3200));
+      p.total = static_cast<long long>(p.jobs) * 3200 * p.rows;
+      p.nb = 1; p.zero = 1; p.delay = delay; p.order = 0; p.counter = counter;
+      p.jitter = jm == 0 ? 0 : (jm == 1 ? delay / 2 : delay * 9 / 10);
+      printf("delay %5d jitter %5d rows 10 :", delay, p.jitter);
+      grid_row<5>(p, sms, ""); grid_row<6>(p, sms, "");
+      printf("\n");
+    }
+  return 0;
+}
+
+int main(int argc, char **argv) {
   const long long H = 1024, W = 1024, N = 100, B = 32;
   const long long RW = W * N;
   const long long total = H * RW * B;   // 3.36 GB
@@ -128,6 +197,8 @@ int main() {
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   float ms;
+  if (argc > 1 && argv[1][0] == 't') return team_grid(dst, counter, sms, total, RW);
+  if (argc > 1 && argv[1][0] == 'j') return jitter_grid(dst, counter, sms, total, RW);
   // 1. cudaMemset
   for (int it = 0; it < 3; ++it) {
     CK(cudaEventRecord(e0));
@@ -163,6 +234,9 @@ int main() {
         p.jobs = static_cast<int>(total / (static_cast<long long>(g.seg) * g.rows));
         p.nb = nb;
         p.zero = zero;
+        p.delay = 0;
+        p.order = 0;
+        p.jitter = 0;
         p.counter = counter;
         const float t2 = run<2>(p, sms, 5);
         const float t4 = run<4>(p, sms, 5);
