@@ -155,6 +155,25 @@ __device__ long long g_team_prof[148 * 32 * 12];
 #define MRX_FLAG(p, bit) 0
 #endif
 
+// The next tile ticket, drawn a tile before it is used.  The counter is kept as a FLOAT while
+// the launch has fewer than 2^24 tiles (tickets are exact): ptxas turns an integer atomic add of
+// a constant into its warp-aggregated form (vote, popc, shuffle), and the shuffle reads the
+// returned value at once, which puts the counter's round trip through a store-saturated L2 on
+// the team's path.  It leaves a float add alone.  Zero is zero in both formats (the reset at the
+// end of every launch, the memset).  Returns raw bits; ticket_value() converts where the ticket
+// is used (a conversion next to the atomic would wait for it).
+__device__ __forceinline__ unsigned draw_ticket(unsigned int *counter, bool as_float) {
+  unsigned v;
+  if (as_float)
+    asm volatile("atom.global.add.f32 %0, [%1], 0f3F800000;" : "=r"(v) : "l"(counter) : "memory");
+  else
+    v = atomicAdd(counter, 1u);
+  return v;
+}
+__device__ __forceinline__ int ticket_value(unsigned raw, bool as_float) {
+  return as_float ? static_cast<int>(__uint_as_float(raw)) : static_cast<int>(raw);
+}
+
 __device__ __forceinline__ void team_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -327,16 +346,23 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
   // ---- prologue of the pipeline: decode the first two tiles, cull the first
   // (the team's last warp decodes, its first warp stores, the ones between cull)
   int cur_b = 0;   // search cursor of decode(); meaningful in the decoding thread only
+  // The decoding lane holds one ticket ahead of the descriptor it fills: the counter's round trip
+  // through an L2 that is saturated with stores takes thousands of cycles (the decode warp used
+  // to reach the tile barrier after the storing warp); drawn a tile early, it is off the path.
+  unsigned ticket = 0u;   // raw bits, see draw_ticket()
+  const bool float_tickets = total < (1 << 24) - 4 * static_cast<int>(gridDim.x) * kTeams;   // (+ the draws past the end)
   if (wt == kTeamWarps - 1 && lane == 0) {
     // tiles are handed out by a global counter (reset by mrx_unmold_prologue): box density
     // varies across the canvas, a static assignment leaves a tail of late teams
-    const int t0 = static_cast<int>(atomicAdd(p.job_counter, 1u));
-    const int t1 = static_cast<int>(atomicAdd(p.job_counter, 1u));
+    const int t0 = ticket_value(draw_ticket(p.job_counter, float_tickets), float_tickets);
+    const int t1 = ticket_value(draw_ticket(p.job_counter, float_tickets), float_tickets);
+    ticket = draw_ticket(p.job_counter, float_tickets);
     dc.b = -1;
     decode(t0, cur_b, &s_job[0]);
     decode(t1, cur_b, &s_job[1]);
     s_ecount[tm][0] = 0;
     s_ecount[tm][1] = 0;
+    if (ticket == 0xffffffffu) p.job_counter[0] = 0u;   // (never true) all three tickets are drawn: see the end
   }
   team_bar(bar_id, kTeamThreads);
   // a team that is done says so; the last one of the grid leaves both scheduler words at zero
@@ -667,7 +693,11 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     } else if (more) {
       if (wt == kTeamWarps - 1) {
         // ---- the descriptor of this tile retires: decode the tile after next into it
-        if (lane == 0) decode(static_cast<int>(atomicAdd(p.job_counter, 1u)), cur_b, &s_job[slot]);
+        if (lane == 0) {
+          const int mine = ticket_value(ticket, float_tickets);
+          ticket = draw_ticket(p.job_counter, float_tickets);   // used one tile from now
+          decode(mine, cur_b, &s_job[slot]);
+        }
         __syncwarp();
         PROF_MARK(7)
       } else {
@@ -677,7 +707,10 @@ mask_expand_team_kernel(const ExpandParams p, const int buf_bytes) {
     if (!more) break;
     slot = nslot;
   }
-  team_bar(bar_id, kTeamThreads);   // the decoding lane's last ticket precedes the retirement
+  // the decoding lane's last ticket must have been drawn before the team retires (the last team
+  // of the grid zeroes the counter): reading its value waits for it
+  if (ticket == 0xffffffffu) p.job_counter[0] = 0u;   // (never true: not a ticket in either format)
+  team_bar(bar_id, kTeamThreads);
   retire();
   PROF_MARK(5)
   PROF_FLUSH
