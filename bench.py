@@ -502,6 +502,8 @@ def run_ours(args, rank, world, local_rank):
     # are node-local (matters for the e2e figure at N = 8: GPUs 4-7 hang off the second socket)
     numa = sharding.bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False}
     if world > 1:
+        # rank 0's stdout carries the one JSON line: NCCL's version banner / debug log goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic inputs (seeded, per rank, 32 DISTINCT images), in HBM and in pinned memory
