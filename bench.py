@@ -136,6 +136,19 @@ def cpu_baseline_block(procs=None, images=None):
     }
 
 
+_RESULT_FD = None
+
+
+def emit_line(line):
+    """The one JSON line, on the process's original stdout (see main())."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU algorithm (oracle port; the reference's
     code for this path is not vendored) on all the host threads it can use."""
@@ -172,7 +185,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -502,8 +515,6 @@ def run_ours(args, rank, world, local_rank):
     # are node-local (matters for the e2e figure at N = 8: GPUs 4-7 hang off the second socket)
     numa = sharding.bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False}
     if world > 1:
-        # rank 0's stdout carries the one JSON line: NCCL's version banner / debug log goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic inputs (seeded, per rank, 32 DISTINCT images), in HBM and in pinned memory
@@ -759,7 +770,7 @@ def run_ours(args, rank, world, local_rank):
             line["gather"] = gather
         if config4 is not None:
             line["config4"] = config4
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -789,6 +800,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    # stdout carries ONE line, the JSON result: whatever libraries print there (NCCL's version
+    # banner at N > 1) goes to stderr; emit_line() writes to the saved descriptor
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args, rank, world)
     return run_ours(args, rank, world, local_rank)
