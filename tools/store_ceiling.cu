@@ -38,6 +38,9 @@ struct P {
   int delay;            // clocks of pretend compute per job (spin) before the store
   int order;            // 0: atomic ticket, 1: static round robin (job = worker + k * workers)
   int jitter;           // delay varies per job: uniform in [delay - jitter, delay + jitter] (hash of the job)
+  int victim;           // 1: the CTA's last warp stores nothing; lane 0 times a shared-memory load, a global
+                        // load and a global atomic, back to back, until the other warps are done
+  unsigned long long *vstats;   // [4]: sum of LDS / LDG / ATOMG cycles, samples
   unsigned int *counter;
 };
 
@@ -51,7 +54,33 @@ __global__ void __launch_bounds__(kWarps * 32, 1) store_kernel(const P p) {
     reinterpret_cast<uint4 *>(mine)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
   int k = 0;
-  const int worker = blockIdx.x * kWarps + warp, workers = gridDim.x * kWarps;
+  __shared__ int s_done;
+  __shared__ int s_word[32];
+  if (threadIdx.x == 0) s_done = 0;
+  if (threadIdx.x < 32) s_word[threadIdx.x] = threadIdx.x;
+  __syncthreads();
+  const int store_warps = p.victim ? kWarps - 1 : kWarps;
+  if (p.victim && warp == kWarps - 1) {
+    // ---- the victim: what do ordinary memory instructions cost while the others store?
+    if (lane == 0) {
+      unsigned long long lds = 0, ldg = 0, atm = 0, n = 0;
+      int idx = 0;
+      while (*reinterpret_cast<volatile int *>(&s_done) < store_warps) {
+        long long t0 = clock64();
+        idx = *reinterpret_cast<volatile int *>(&s_word[idx & 31]);
+        long long t1 = clock64();
+        const unsigned g = *reinterpret_cast<volatile unsigned *>(p.counter + 1 + (idx & 1));
+        long long t2 = clock64();
+        const unsigned a = atomicAdd(p.counter + 4, g & 0u) ;
+        long long t3 = clock64() + (a & 0u);
+        lds += t1 - t0; ldg += t2 - t1; atm += t3 - t2; ++n;
+        __nanosleep(200);
+      }
+      atomicAdd(p.vstats + 0, lds); atomicAdd(p.vstats + 1, ldg); atomicAdd(p.vstats + 2, atm); atomicAdd(p.vstats + 3, n);
+    }
+    return;
+  }
+  const int worker = blockIdx.x * store_warps + warp, workers = gridDim.x * store_warps;
   while (true) {
     int j = 0;
     if (p.order == 1) {
@@ -99,7 +128,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) store_kernel(const P p) {
     }
     ++k;
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (lane == 0) {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    atomicAdd(&s_done, 1);
+  }
 }
 
 __global__ void plain_fill(uint4 *dst, long long n16) {
@@ -152,7 +184,7 @@ static int team_grid(unsigned char *dst, unsigned int *counter, int sms, long lo
         p.band_bytes = rows * RW;
         p.jobs = static_cast<int>((1024 / rows) * 32 * (RW / 3200));   // whole bands only
         p.total = static_cast<long long>(p.jobs) * 3200 * rows;
-        p.nb = 1; p.zero = 1; p.delay = delay; p.order = order; p.jitter = 0; p.counter = counter;
+        p.nb = 1; p.zero = 1; p.delay = delay; p.order = order; p.jitter = 0; p.victim = 0; p.vstats = nullptr; p.counter = counter;
         // bands of one image follow each other; images are 1024 rows apart
         printf("order %d delay %5d rows %2d :", order, delay, rows);
         grid_row<2>(p, sms, ""); grid_row<3>(p, sms, ""); grid_row<4>(p, sms, "");
@@ -173,11 +205,45 @@ static int jitter_grid(unsigned char *dst, unsigned int *counter, int sms, long 
       p.band_bytes = p.rows * RW;
       p.jobs = static_cast<int>((1024 / p.rows) * 32 * (RW / 3200));
       p.total = static_cast<long long>(p.jobs) * 3200 * p.rows;
-      p.nb = 1; p.zero = 1; p.delay = delay; p.order = 0; p.counter = counter;
+      p.nb = 1; p.zero = 1; p.delay = delay; p.order = 0; p.victim = 0; p.vstats = nullptr; p.counter = counter;
       p.jitter = jm == 0 ? 0 : (jm == 1 ? delay / 2 : delay * 9 / 10);
       printf("delay %5d jitter %5d rows 10 :", delay, p.jitter);
       grid_row<5>(p, sms, ""); grid_row<6>(p, sms, "");
       printf("\n");
+    }
+  return 0;
+}
+
+// mode `v`: 6 storing warps + 1 victim warp per SM; 32000-byte jobs as 10 x 3200 B row segments (the team
+// kernel's tile), as 1 x 32000 B and as 2 x 16000 B; pretend compute 0 / 4000 clocks
+static int victim_grid(unsigned char *dst, unsigned int *counter, int sms, long long RW) {
+  unsigned long long *vs;
+  CK(cudaMalloc(&vs, 32));
+  struct G { int seg, rows; long long stride; };
+  const G gs[] = {{3200, 10, RW}, {32000, 1, 32000}, {16000, 2, 16000}, {6400, 5, 6400}};
+  for (const G &g : gs)
+    for (int delay : {0, 4000, 5800}) {
+      P p;
+      p.dst = dst; p.seg = g.seg; p.rows = g.rows; p.row_stride = g.stride;
+      if (g.rows == 10) {
+        p.segs_per_row = static_cast<int>(RW / 3200);
+        p.band_bytes = 10 * RW;
+        p.jobs = (1024 / 10) * 32 * p.segs_per_row;
+      } else {   // contiguous jobs
+        p.segs_per_row = 1;
+        p.band_bytes = 32000;
+        p.jobs = 104000;
+      }
+      p.total = static_cast<long long>(p.jobs) * 32000;
+      p.nb = 1; p.zero = 1; p.delay = delay; p.order = 0; p.jitter = 0; p.victim = 1; p.vstats = vs; p.counter = counter;
+      CK(cudaMemset(vs, 0, 32));
+      CK(cudaMemset(counter, 0, 32));
+      const float t = run<7>(p, sms, 3);
+      unsigned long long h[4];
+      CK(cudaMemcpy(h, vs, 32, cudaMemcpyDeviceToHost));
+      const double n = h[3] ? static_cast<double>(h[3]) : 1.0;
+      printf("seg %5d x %2d delay %5d : %.4f ms (%.0f GB/s)   victim LDS %.0f  LDG %.0f  ATOMG %.0f clocks (n=%llu)\n", g.seg,
+             g.rows, delay, t, p.total / t / 1e6, h[0] / n, h[1] / n, h[2] / n, h[3]);
     }
   return 0;
 }
@@ -189,7 +255,8 @@ int main(int argc, char **argv) {
   unsigned char *dst;
   unsigned int *counter;
   CK(cudaMalloc(&dst, total));
-  CK(cudaMalloc(&counter, 4));
+  CK(cudaMalloc(&counter, 64));
+  CK(cudaMemset(counter, 0, 64));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
@@ -199,6 +266,7 @@ int main(int argc, char **argv) {
   float ms;
   if (argc > 1 && argv[1][0] == 't') return team_grid(dst, counter, sms, total, RW);
   if (argc > 1 && argv[1][0] == 'j') return jitter_grid(dst, counter, sms, total, RW);
+  if (argc > 1 && argv[1][0] == 'v') return victim_grid(dst, counter, sms, RW);
   // 1. cudaMemset
   for (int it = 0; it < 3; ++it) {
     CK(cudaEventRecord(e0));
@@ -237,6 +305,8 @@ int main(int argc, char **argv) {
         p.delay = 0;
         p.order = 0;
         p.jitter = 0;
+        p.victim = 0;
+        p.vstats = nullptr;
         p.counter = counter;
         const float t2 = run<2>(p, sms, 5);
         const float t4 = run<4>(p, sms, 5);
