@@ -13,7 +13,8 @@
 // restricting every block of pixels to the instances whose box meets it (0.947 ms: slower), and
 // persistent CTAs with a two-stage bulk-copy ring (0.96 ms: four resident CTAs per SM are too
 // few threads for the divergent walk; time went as 1/CTAs).  What did pay: replacing the
-// load-and-store staging loop by ONE bulk copy per block (0.886 -> 0.653 ms).
+// load-and-store staging loop by ONE bulk copy per block (0.886 -> 0.653 ms), and the blend
+// constants' load loop by a second one (-> 0.623 ms).
 //
 // HBM-read bound: N bytes of canvas per pixel (3.36 GB per config-2 batch) + 3 B in + 3 B out.
 // One CTA = 256 consecutive pixels of one image: their 256*N canvas bytes are contiguous
@@ -35,7 +36,8 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
                        const int *__restrict__ counts, const int *__restrict__ geom,
                        const int4 *__restrict__ boxes, const unsigned char *__restrict__ images,
                        const long long *__restrict__ image_off, const double *__restrict__ blend,
-                       double one_minus_alpha, unsigned char *__restrict__ out, int R) {
+                       double one_minus_alpha, unsigned char *__restrict__ out, int R,
+                       int blend_bulk) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int b = blockIdx.y;
   const int H = geom[b * MRX_GEOM_INTS + 0], W = geom[b * MRX_GEOM_INTS + 1];
@@ -62,16 +64,23 @@ composite_masks_kernel(const unsigned char *__restrict__ canvas,
     fence_mbar_init();
   }
   if (t < 32) __syncwarp();
+  // the image's blend constants (N x 3 doubles) come the same way when every image's block of
+  // the [B,R,3] array starts 16-byte aligned (blend_bulk: R even, base aligned); otherwise the
+  // threads load them
   if (t == 0) {
-    if (bytes) {
-      mbar_arrive_expect_tx(&s_bar, bytes);
-      bulk_g2s(s_can, canvas + canvas_off[b] + static_cast<size_t>(p0) * N, bytes, &s_bar);
+    const unsigned cbytes = blend_bulk ? (static_cast<unsigned>(N) * 24u + 15u) & ~15u : 0u;
+    if (bytes + cbytes) {
+      mbar_arrive_expect_tx(&s_bar, bytes + cbytes);
+      if (bytes) bulk_g2s(s_can, canvas + canvas_off[b] + static_cast<size_t>(p0) * N, bytes, &s_bar);
+      if (cbytes) bulk_g2s(s_blend, blend + static_cast<size_t>(b) * R * 3, cbytes, &s_bar);
     } else {
       mbar_arrive(&s_bar);
     }
   }
-  for (int i = t; i < N * 3; i += kCompThreads)
-    s_blend[i] = blend[static_cast<size_t>(b) * R * 3 + i];
+  if (!blend_bulk) {
+    for (int i = t; i < N * 3; i += kCompThreads)
+      s_blend[i] = blend[static_cast<size_t>(b) * R * 3 + i];
+  }
   for (int i = t; i < N; i += kCompThreads) {
     const int4 bx = boxes[static_cast<size_t>(b) * R + i];
     s_skip[i] = (bx.x | bx.y | bx.z | bx.w) == 0;   // upstream: `if not np.any(boxes[i]): continue`
@@ -155,7 +164,8 @@ extern "C" int mrx_composite_masks(const unsigned char *d_canvas, const long lon
   dim3 grid(static_cast<unsigned>(blocks), static_cast<unsigned>(B));
   composite_masks_kernel<<<grid, kCompThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       d_canvas, d_canvas_off, d_counts, d_geom, reinterpret_cast<const int4 *>(d_boxes), d_images,
-      d_image_off, d_blend, one_minus_alpha, d_out, R);
+      d_image_off, d_blend, one_minus_alpha, d_out, R,
+      ((R & 1) == 0 && (reinterpret_cast<uintptr_t>(d_blend) & 15u) == 0u) ? 1 : 0);
   MRX_LAUNCH_CHECK("composite_masks_kernel");
   return MRX_OK;
 }
