@@ -19,7 +19,7 @@
 // HBM-read bound: N bytes of canvas per pixel (3.36 GB per config-2 batch) + 3 B in + 3 B out.
 // One CTA = 256 consecutive pixels of one image: their 256*N canvas bytes are contiguous
 // (N innermost) and are brought into shared memory by a single 1-D bulk copy (TMA, completion
-// on an mbarrier) issued by thread 0 while the CTA loads its blend constants; eight CTAs are
+// on an mbarrier) issued by thread 0, the image's blend constants by a second one; eight CTAs are
 // resident per SM, so ~200 KB of copies are in flight per SM.  Thread t then walks pixel t's
 // N bytes (4 at a time when N % 4 == 0: most words are zero) and applies the blends of the set
 // instances in instance order -- fp64 with explicit _rn intrinsics in NumPy's operation
