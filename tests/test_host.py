@@ -267,3 +267,21 @@ def test_no_unbound_global_names_in_the_package():
                 bound.add(node.name)
         used = {n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
         assert not (used - bound), (os.path.basename(path), sorted(used - bound))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """Contract of bench.py: rank 0's stdout carries exactly ONE line, the JSON result (library
+    banners and worker output go to stderr).  The reference arm runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "0", "--cpu-procs", "2"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "instance-masks/sec"
+    assert line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 2
